@@ -1,0 +1,170 @@
+/*
+ * sparsefusion_b200.h -- C ABI of libsparsefusion_b200.so
+ *
+ * The drop-in boundary of the B200-native SparseFusion hot path.  Every entry point takes plain
+ * DEVICE pointers (fp32 / int32 / uint8, contiguous), sizes and a CUDA stream handle
+ * (`void* stream` == cudaStream_t; NULL == the legacy default stream); there are no torch types in
+ * any signature.  Each function replaces one binding of the reference's pybind operator modules
+ * or one nn.Module hot loop; the comment above each declaration cites the reference interface
+ * (file:line relative to zhizdev/sparsefusion) it stands in for.
+ *
+ * Conventions (same as the reference operators, raymarching/src/bindings.cpp, gridencoder/src/bindings.cpp):
+ *   - the CALLER allocates every output and passes it in; nothing is allocated or freed inside;
+ *   - launches are asynchronous on `stream`; errors that CUDA reports at launch time are returned,
+ *     asynchronous faults surface at the caller's next synchronisation, as with the reference;
+ *   - return value 0 == success; non-zero == SFB_ERR_* and sfb_last_error() holds a message
+ *     (the Python host raises RuntimeError with it, mirroring TORCH_CHECK in gridencoder.cu:425-441);
+ *   - dtype is fp32 only: the reference dispatches half/double too but never calls them
+ *     (custom_fwd(cast_inputs=float32), raymarching.py:21 and SURVEY.md §2.3).
+ */
+#ifndef SPARSEFUSION_B200_H
+#define SPARSEFUSION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+#define SFB_OK 0
+#define SFB_ERR_ARG 1
+#define SFB_ERR_CUDA 2
+#define SFB_ERR_UNSUPPORTED 3
+
+const char* sfb_last_error(void);
+int sfb_abi_version(void);
+int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ============================================================================================
+ * 1. `_gridencoder` operator module      (external/gridencoder/src/bindings.cpp:5-8)
+ * ========================================================================================== */
+
+/* grid_encode_forward  -- gridencoder.h:12, gridencoder.cu:424-447 (kernel_grid :75-223).
+ * inputs [B,D] in [0,1]; embeddings [rows,C]; offsets [L+1] int32; outputs [L,B,C] (pre-allocated);
+ * S = log2(per_level_scale); H = base resolution; dy_dx [B,L*D*C] or NULL;
+ * gridtype 0 = hash, 1 = tiled.  D in 1..5, C in {1,2,4,8} as in the reference. */
+int sfb_grid_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float* dy_dx,
+                            uint32_t gridtype, int align_corners, void* stream);
+
+/* grid_encode_backward -- gridencoder.h:13, gridencoder.cu:449-479 (kernel_grid_backward :226-313,
+ * kernel_input_backward :316-342).  grad [L,B,C]; grad_embeddings [rows,C] must be pre-ZEROED by the
+ * caller (grid.py:72); dy_dx / grad_inputs [B,D] may both be NULL. */
+int sfb_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int32_t* offsets,
+                             float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                             uint32_t H, const float* dy_dx, float* grad_inputs, uint32_t gridtype,
+                             int align_corners, void* stream);
+
+/* Parity instrumentation (no reference counterpart): the per-level scale exactly as the device
+ * computes it (gridencoder.cu:125, device exp2f) -> scales[L]; and the absolute embedding-row index of
+ * every interpolation corner -> rows [L,B,2^D] int32 (-1 for out-of-range points), so that the
+ * "bit-exact grid indexing" contract can be tested directly against the oracle. */
+int sfb_grid_level_scales(uint32_t L, float S, uint32_t H, float* scales, void* stream);
+int sfb_grid_corner_rows(const float* inputs, const int32_t* offsets, int32_t* rows, uint32_t B, uint32_t D,
+                         uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, void* stream);
+
+/* ============================================================================================
+ * 2. `_raymarching` operator module      (raymarching/src/bindings.cpp:5-18, raymarching.h:7-17)
+ *    Argument order is the reference's, with tensors replaced by device pointers.
+ * ========================================================================================== */
+
+/* raymarching.cu:148-156 (kernel :91-145).  rays_o/d [N,3], aabb [6] -> nears/fars [N]; misses get FLT_MAX */
+int sfb_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                           float* nears, float* fars, void* stream);
+/* raymarching.cu:201-209 (kernel :162-198).  -> coords [N,2] */
+int sfb_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream);
+/* raymarching.cu:229-232 (kernel :214-226).  coords [N,3] int32 -> indices [N] int32 */
+int sfb_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+/* raymarching.cu:257-260 (kernel :237-254) */
+int sfb_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+/* raymarching.cu:292-300 (kernel :267-289).  grid [N*8] floats -> bitfield [N] bytes */
+int sfb_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream);
+/* raymarching.cu:482-490 (kernel :311-480).  grid = density bitfield [C*H^3/8]; xyzs/dirs [M,3], deltas [M,2],
+ * rays [N,3] int32 (ray id, point offset, count), counter [2] int32 (points, rays; caller zeroes), noises [N] */
+int sfb_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                         const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                         const float* noises, void* stream);
+/* raymarching.cu:580-588 (kernel :500-577) */
+int sfb_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                     uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                     float* image, void* stream);
+/* raymarching.cu:685-693 (kernel :601-682).  grad_sigmas [M] / grad_rgbs [M,3] pre-zeroed by the caller */
+int sfb_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                      const float* rgbs, const float* deltas, const int32_t* rays,
+                                      const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                      float T_thresh, float* grad_sigmas, float* grad_rgbs, void* stream);
+/* raymarching.cu:808-815 (kernel :700-805) */
+int sfb_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                   uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs,
+                   float* deltas, const float* noises, void* stream);
+/* raymarching.cu:908-914 (kernel :818-905); in place on rays_alive / rays_t / weights_sum / depth / image */
+int sfb_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                       const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                       float* image, void* stream);
+
+/* ============================================================================================
+ * 3. VLDM UNet forward operators        (external/imagen_pytorch.py Unet, :1078-1671)
+ *    Activations are NHWC fp32 ([NB,H,W,ld] with a channel stride `ld` so that a call can read or
+ *    write a channel slice of a wider tensor).  The reference runs these as ~600 eager PyTorch
+ *    launches per forward (cuDNN / cuBLAS in TF32); here they are the operators the host-side
+ *    `Unet` module (sparsefusion_b200/imagen_pytorch.py) strings together.
+ * ========================================================================================== */
+
+/* nn.Conv2d / nn.Linear as implicit GEMM on tcgen05 tensor cores (kind::tf32, fp32 accumulate), TMA-fed.
+ * Stands in for Block.project (:652), res_conv (:708), Downsample (:608-610), PixelShuffleUpsample conv
+ * (:586), CrossEmbedLayer convs (:1038), ChanFeedForward 1x1 convs (:957,:960), final_conv (:1386) and the
+ * token projections of Attention / CrossAttention when there are many tokens.
+ *   x        [NB,H,W,ldx] NHWC, Cin channels used          w_packed [Cout][KH*KW][ceil32(Cin)] (sfb_conv_weight_k floats per
+ *   row; TF32-rounded, zero padded; tap-major then channel)          bias [Cout] or NULL          residual [NB,Ho,Wo,ldr] or NULL
+ *   out      [NB,Ho,Wo,ldo]; accumulate != 0 adds into `out` (red.global.add) instead of storing
+ *   splits   K-range split across CTAs (0 = choose so that ~all SMs stream weights); bn: N tile (0 = auto; 32/64/128/256)
+ * stride 1 or 2, any odd/even kernel with symmetric `pad`.  Cin, Cout, ldx, ldo multiples of 4. */
+int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW,
+                         int stride, int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                         int accumulate, int splits, int bn, void* stream);
+int sfb_conv_weight_k(int Cin, int KH, int KW);
+/* experiment switch: encode activation/weight tensor maps as TFLOAT32 instead of FLOAT32 */
+int sfb_conv_set_tma_tf32(int enable);
+
+/* layout at the module boundary (the reference API is NCHW): NCHW [NB,C,H,W] <-> channel slice of NHWC */
+int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream);
+int sfb_nhwc_to_nchw(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, void* stream);
+/* torch.cat((x, skip * scale), dim=1) of the up path (:1639) */
+int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2, int64_t ldb, float scale_b, float* out, int64_t ldo,
+                     int64_t npix, void* stream);
+/* nn.SiLU + nn.PixelShuffle(2) of PixelShuffleUpsample (:588-592): y [NB,H,W,4*Co] -> out [NB,2H,2W,ldo] */
+int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
+/* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
+ * stats_ws: NB*G*2 floats of workspace.  Output is TF32-rounded (it feeds the conv). */
+int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
+                       int64_t film_ld, int act_silu, float eps, float* stats_ws, float* y, int64_t ldy, void* stream);
+/* LayerNorm / ChanLayerNorm (:301-329; gain g, optional bias b for nn.LayerNorm) over the last dim of [T,C] rows,
+ * optionally of GELU(x) (ChanFeedForward :958-959), optionally + res (the `attn(x) + x` of :986) */
+int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
+                       int C, int pre_gelu, int round_tf32, void* stream);
+/* nn.Linear for few rows (time MLPs :683-686, to_time_* :1175-1190, GlobalContext.net :929-934, token projections at 4x4):
+ * y = post(bias + pre(x) W^T) + res; pre 0|1(SiLU), post 0|1(SiLU)|2(sigmoid); W [O,K] row-major (nn.Linear layout) */
+int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* bias, const float* res, int64_t ldr, float* y, int64_t ldy,
+                     int M, int K, int O, int pre, int post, int round_tf32, void* stream);
+/* LearnedSinusoidalPosEmb (:634-639): out [B, 2*half+1] */
+int sfb_time_fourier(const float* t, const float* w, float* out, int B, int half, void* stream);
+/* softmax(QK^T)V cores: multi-query self attention with null and context keys (:517-566) and cross attention (:770-805) */
+int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, const float* ckv, float* out, int B, int n, int heads, int dh,
+                     int nc, float scale, void* stream);
+int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, float* out, int B, int n, int heads, int dh, int nc,
+                        float scale, void* stream);
+/* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW floats */
+int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
+                 void* stream);
+/* ResnetBlock tail (:727-729): out = h * gate[n][c] + res (gate NULL == 1) */
+int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const float* res, int64_t ldr, float* out, int64_t ldo, int NB,
+                           int HW, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSEFUSION_B200_H */

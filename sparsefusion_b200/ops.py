@@ -1,0 +1,216 @@
+"""Torch-tensor front ends of the UNet operators of the C ABI (include/sparsefusion_b200.h §3).
+
+Everything here is plumbing: allocate outputs with torch, pass device pointers + the current
+stream to libsparsefusion_b200.so.  Activations are NHWC fp32 tensors ``[NB, H, W, C]``; a
+"channel slice" view ``t[..., a:b]`` of a wider NHWC tensor is accepted wherever a leading
+dimension is passed (its ``stride(2)`` is the channel stride).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as lib
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest (ties away from zero) fp32 -> tf32 kept in fp32 storage (== cvt.rna.tf32.f32)"""
+    i = t.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF)
+    # values whose exponent is all ones (inf / nan) must not be touched
+    keep = (i & 0x7F800000) == 0x7F800000
+    return torch.where(keep, i, r).view(torch.float32)
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,Cin,KH,KW] (or nn.Linear weight [O,K]) -> [Cout, KH*KW*ceil32(Cin)]
+    tap-major / channel-minor, zero padded, TF32-rounded: the K-major B operand of the implicit GEMM."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    cout, cin, kh, kw = w.shape
+    cin_pad = (cin + 31) // 32 * 32
+    p = torch.zeros(cout, kh, kw, cin_pad, dtype=torch.float32, device=w.device)
+    p[..., :cin] = w.detach().float().permute(0, 2, 3, 1)
+    return round_tf32(p.reshape(cout, kh * kw * cin_pad)).contiguous()
+
+
+def _nhwc_meta(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
+    """(NB, H, W, C, ld) of an NHWC tensor or channel-slice view of one"""
+    assert t.dim() == 4 and t.is_cuda and t.dtype == torch.float32, 'expected a CUDA fp32 NHWC tensor'
+    nb, h, w, c = t.shape
+    ld = t.stride(2)
+    assert t.stride(3) == 1 and t.stride(1) == w * ld and t.stride(0) == h * w * ld, 'expected NHWC with a uniform channel stride'
+    return nb, h, w, c, ld
+
+
+def _rows_meta(t: torch.Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a row-major 2D-like tensor [..., C] with uniform row stride"""
+    assert t.is_cuda and t.dtype == torch.float32 and t.stride(-1) == 1
+    c = t.shape[-1]
+    rows = t.numel() // c
+    ld = t.stride(-2) if t.dim() >= 2 else c
+    return rows, c, ld
+
+
+# --------------------------------------------------------------------------------------------- conv / linear on tensor cores
+def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
+                bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                accumulate: bool = False, splits: int = 0, bn: int = 0) -> torch.Tensor:
+    nb, h, w, cin, ldx = _nhwc_meta(x)
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty(nb, ho, wo, cout, dtype=torch.float32, device=x.device)
+    onb, oh, ow, oc, ldo = _nhwc_meta(out)
+    assert (onb, oh, ow, oc) == (nb, ho, wo, cout), f'out shape {tuple(out.shape)} != {(nb, ho, wo, cout)}'
+    assert w_packed.shape == (cout, kh * kw * ((cin + 31) // 32 * 32)), 'packed weight shape mismatch'
+    ldr = 0
+    if residual is not None:
+        rnb, rh, rw, rc, ldr = _nhwc_meta(residual)
+        assert (rnb, rh, rw, rc) == (nb, ho, wo, cout)
+    lib.call('sfb_conv2d_nhwc_tf32', x.data_ptr(), nb, h, w, cin, ldx,
+             lib.fptr(w_packed, 'w_packed'), cout, kh, kw, stride, pad, lib.fptr(bias, 'bias'),
+             None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
+    return out
+
+
+def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=None, residual=None, out=None) -> torch.Tensor:
+    """nn.Linear on the tensor cores: rows [T, K] are treated as T 1x1 'images'"""
+    t, k, ld = _rows_meta(x)
+    x4 = x.as_strided((t, 1, 1, k), (ld, ld, ld, 1))
+    if out is None:
+        out = torch.empty(*x.shape[:-1], out_features, dtype=torch.float32, device=x.device)
+    to, co, ldo = _rows_meta(out)
+    o4 = out.as_strided((t, 1, 1, out_features), (ldo, ldo, ldo, 1))
+    r4 = None
+    if residual is not None:
+        tr, cr, ldr = _rows_meta(residual)
+        r4 = residual.as_strided((t, 1, 1, out_features), (ldr, ldr, ldr, 1))
+    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4)
+    return out
+
+
+# --------------------------------------------------------------------------------------------- layout
+def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, c_off: int = 0, round_to_tf32: bool = False) -> torch.Tensor:
+    nb, c, h, w = src.shape
+    dnb, dh, dw, dc, ld = _nhwc_meta(dst)
+    assert (dnb, dh, dw) == (nb, h, w) and c_off + c <= dc
+    lib.call('sfb_nchw_to_nhwc', lib.fptr(src.contiguous(), 'src'), dst.data_ptr(), nb, c, h, w, ld, c_off, int(round_to_tf32), lib.stream())
+    return dst
+
+
+def nhwc_to_nchw(src: torch.Tensor) -> torch.Tensor:
+    nb, h, w, c, ld = _nhwc_meta(src)
+    dst = torch.empty(nb, c, h, w, dtype=torch.float32, device=src.device)
+    lib.call('sfb_nhwc_to_nchw', src.data_ptr(), lib.fptr(dst), nb, c, h, w, ld, lib.stream())
+    return dst
+
+
+def concat2(a: torch.Tensor, b: torch.Tensor, scale_b: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nb, h, w, c1, lda = _nhwc_meta(a)
+    _, _, _, c2, ldb = _nhwc_meta(b)
+    if out is None:
+        out = torch.empty(nb, h, w, c1 + c2, dtype=torch.float32, device=a.device)
+    ldo = _nhwc_meta(out)[4]
+    lib.call('sfb_concat2_nhwc', a.data_ptr(), c1, lda, b.data_ptr(), c2, ldb, float(scale_b), out.data_ptr(), ldo, nb * h * w, lib.stream())
+    return out
+
+
+def pixel_shuffle_silu(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nb, h, w, c4, ld = _nhwc_meta(y)
+    assert ld == c4 and c4 % 4 == 0
+    co = c4 // 4
+    if out is None:
+        out = torch.empty(nb, 2 * h, 2 * w, co, dtype=torch.float32, device=y.device)
+    ldo = _nhwc_meta(out)[4]
+    lib.call('sfb_pixel_shuffle_silu_nhwc', y.data_ptr(), out.data_ptr(), nb, h, w, co, ldo, lib.stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- norms
+def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor, film: Optional[torch.Tensor] = None,
+              silu: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nb, h, w, c, ldx = _nhwc_meta(x)
+    if out is None:
+        out = torch.empty(nb, h, w, c, dtype=torch.float32, device=x.device)
+    ldy = _nhwc_meta(out)[4]
+    ws = torch.empty(nb * groups * 2, dtype=torch.float32, device=x.device)
+    film_ld = 0
+    if film is not None:
+        assert film.shape == (nb, 2 * c) and film.stride(1) == 1
+        film_ld = film.stride(0)
+    lib.call('sfb_groupnorm_nhwc', x.data_ptr(), ldx, nb, h * w, c, groups, lib.fptr(gamma), lib.fptr(beta), None if film is None else film.data_ptr(),
+             film_ld, int(silu), float(eps),
+             lib.fptr(ws), out.data_ptr(), ldy, lib.stream())
+    return out
+
+
+def layernorm(x: torch.Tensor, g: torch.Tensor, b: Optional[torch.Tensor] = None, pre_gelu: bool = False, round_to_tf32: bool = True,
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    t, c, ldx = _rows_meta(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    ldy = _rows_meta(out)[2]
+    ldr = _rows_meta(residual)[2] if residual is not None else 0
+    lib.call('sfb_layernorm_rows', x.data_ptr(), ldx, lib.fptr(g.reshape(-1)), lib.fptr(b), None if residual is None else residual.data_ptr(), ldr,
+             out.data_ptr(), ldy, t, c, int(pre_gelu), int(round_to_tf32), lib.stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- small linears / misc
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias=None, pre: int = 0, post: int = 0, residual=None, round_to_tf32: bool = False,
+                 out=None) -> torch.Tensor:
+    m, k, ldx = _rows_meta(x)
+    o = w.shape[0]
+    assert w.shape[1] == k and w.is_contiguous()
+    if out is None:
+        out = torch.empty(*x.shape[:-1], o, dtype=torch.float32, device=x.device)
+    ldy = _rows_meta(out)[2]
+    ldr = _rows_meta(residual)[2] if residual is not None else 0
+    lib.call('sfb_linear_small', x.data_ptr(), ldx, lib.fptr(w), lib.fptr(bias), None if residual is None else residual.data_ptr(), ldr,
+             out.data_ptr(), ldy, m, k, o, pre, post, int(round_to_tf32), lib.stream())
+    return out
+
+
+def time_fourier(t: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    b, half = t.shape[0], w.shape[0]
+    out = torch.empty(b, 2 * half + 1, dtype=torch.float32, device=t.device)
+    lib.call('sfb_time_fourier', lib.fptr(t.contiguous()), lib.fptr(w), lib.fptr(out), b, half, lib.stream())
+    return out
+
+
+def mq_attention(q, kv, null_kv, ckv, heads: int, dh: int) -> torch.Tensor:
+    b, n = q.shape[0], q.shape[1]
+    nc = 0 if ckv is None else ckv.shape[1]
+    out = torch.empty(b, n, heads * dh, dtype=torch.float32, device=q.device)
+    lib.call('sfb_mq_attention', lib.fptr(q), lib.fptr(kv), lib.fptr(null_kv), lib.fptr(ckv), lib.fptr(out), b, n, heads, dh, nc, float(dh ** -0.5),
+             lib.stream())
+    return out
+
+
+def cross_attention(q, kvc, null_kv, heads: int, dh: int) -> torch.Tensor:
+    b, n = q.shape[0], q.shape[1]
+    nc = kvc.shape[1]
+    out = torch.empty(b, n, heads * dh, dtype=torch.float32, device=q.device)
+    lib.call('sfb_cross_attention', lib.fptr(q), lib.fptr(kvc), lib.fptr(null_kv), lib.fptr(out), b, n, heads, dh, nc, float(dh ** -0.5), lib.stream())
+    return out
+
+
+def gca_pool(x: torch.Tensor, wk: torch.Tensor, bk: torch.Tensor) -> torch.Tensor:
+    nb, h, w, c, ldx = _nhwc_meta(x)
+    ws = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
+    pooled = torch.empty(nb, c, dtype=torch.float32, device=x.device)
+    lib.call('sfb_gca_pool', x.data_ptr(), ldx, nb, h * w, c, lib.fptr(wk.reshape(-1)), lib.fptr(bk), lib.fptr(ws), lib.fptr(pooled), lib.stream())
+    return pooled
+
+
+def gate_residual(h: torch.Tensor, gate: Optional[torch.Tensor], res: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nb, hh, ww, c, ldh = _nhwc_meta(h)
+    ldr = _nhwc_meta(res)[4]
+    if out is None:
+        out = torch.empty(nb, hh, ww, c, dtype=torch.float32, device=h.device)
+    ldo = _nhwc_meta(out)[4]
+    lib.call('sfb_gate_residual_nhwc', h.data_ptr(), ldh, lib.fptr(gate), res.data_ptr(), ldr, out.data_ptr(), ldo, nb, hh * ww, c, lib.stream())
+    return out

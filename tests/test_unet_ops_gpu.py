@@ -1,0 +1,141 @@
+"""Non-GEMM UNet operators (sparsefusion_b200/csrc/unet_ops.cu) against plain PyTorch fp32/fp64 references.
+
+Tolerance: these kernels are fp32; outputs that feed a tensor-core GEMM are TF32-rounded on write, so
+those are compared at 2^-11 relative (+ fp32 noise); everything else at 1e-5.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TF32 = 2.0 ** -11 * 1.01
+
+
+def _close(a, b, rtol, atol=1e-6):
+    err = (a.double() - b.double()).abs()
+    assert (err <= atol + rtol * b.double().abs()).all(), f'max err {err.max().item():.3e} (ref max {b.abs().max().item():.3e})'
+
+
+def test_layout_roundtrip_and_concat():
+    from sparsefusion_b200 import ops
+    x = torch.randn(2, 12, 16, 16, device='cuda')
+    dst = torch.zeros(2, 16, 16, 20, device='cuda')
+    ops.nchw_to_nhwc(x, dst, c_off=8)
+    assert torch.equal(dst[..., 8:], x.permute(0, 2, 3, 1)) and (dst[..., :8] == 0).all()
+    assert torch.equal(ops.nhwc_to_nchw(dst[..., 8:]), x)
+    a, b = torch.randn(2, 4, 4, 8, device='cuda'), torch.randn(2, 4, 4, 12, device='cuda')
+    assert torch.equal(ops.concat2(a, b, 0.5), torch.cat((a, b * 0.5), dim=-1))
+
+
+def test_pixel_shuffle_silu():
+    from sparsefusion_b200 import ops
+    y = torch.randn(2, 4, 4, 32, device='cuda')
+    ref = F.pixel_shuffle(F.silu(y.permute(0, 3, 1, 2)), 2).permute(0, 2, 3, 1)
+    _close(ops.pixel_shuffle_silu(y), ref, 1e-5)
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8)])
+@pytest.mark.parametrize('film', [False, True])
+def test_groupnorm_film_silu(shape, film):
+    from sparsefusion_b200 import ops
+    nb, h, w, c, g = shape
+    x = torch.randn(nb, h, w, c, device='cuda') * 3 + 0.7
+    gamma, beta = torch.randn(c, device='cuda'), torch.randn(c, device='cuda')
+    fm = torch.randn(nb, 2 * c, device='cuda') if film else None
+    y = ops.groupnorm(x, g, gamma, beta, fm, silu=True)
+    ref = F.group_norm(x.permute(0, 3, 1, 2).double(), g, gamma.double(), beta.double(), eps=1e-5)
+    if film:
+        sc, sh = fm.double()[:, :c, None, None], fm.double()[:, c:, None, None]
+        ref = ref * (sc + 1) + sh
+    ref = F.silu(ref).permute(0, 2, 3, 1).float()
+    _close(y, ref, TF32, 2e-5)
+    assert ((y.view(torch.int32) & 0x1FFF) == 0).all(), 'GroupNorm output must be TF32-rounded'
+
+
+def test_layernorm_variants():
+    from sparsefusion_b200 import ops
+    x = torch.randn(37, 256, device='cuda') * 2 + 1
+    g, b = torch.randn(256, device='cuda'), torch.randn(256, device='cuda')
+    ref = F.layer_norm(x.double(), (256,), g.double(), b.double(), eps=1e-5).float()
+    _close(ops.layernorm(x, g, b, round_to_tf32=False), ref, 1e-5, 1e-5)
+    refg = F.layer_norm(F.gelu(x.double()), (256,), g.double(), None, eps=1e-5).float()
+    _close(ops.layernorm(x, g, None, pre_gelu=True, round_to_tf32=False), refg, 1e-5, 1e-5)
+    _close(ops.layernorm(x, g, None, pre_gelu=True, round_to_tf32=True), refg, TF32, 1e-5)
+
+
+@pytest.mark.parametrize('m,k,o', [(1, 1024, 512), (2, 17, 1024), (8, 1024, 2048), (16, 256, 128), (3, 512, 300)])
+def test_linear_small(m, k, o):
+    from sparsefusion_b200 import ops
+    x, w, b = torch.randn(m, k, device='cuda'), torch.randn(o, k, device='cuda') / k ** 0.5, torch.randn(o, device='cuda')
+    res = torch.randn(m, o, device='cuda')
+    ref = F.silu(F.linear(F.silu(x.double()), w.double(), b.double())).float() + res
+    _close(ops.linear_small(x, w, b, pre=1, post=1, residual=res), ref, 1e-5, 1e-5)
+    ref2 = torch.sigmoid(F.linear(x.double(), w.double(), None)).float()
+    _close(ops.linear_small(x, w, None, pre=0, post=2), ref2, 1e-5, 1e-5)
+
+
+def test_time_fourier():
+    from sparsefusion_b200 import ops
+    t = torch.tensor([-3.2, 0.0, 5.7], device='cuda')
+    w = torch.randn(8, device='cuda')
+    f = t[:, None] * w[None, :] * 2 * math.pi
+    ref = torch.cat((t[:, None], f.sin(), f.cos()), dim=-1)
+    _close(ops.time_fourier(t, w), ref, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize('nc', [0, 2])
+def test_mq_attention(nc):
+    from sparsefusion_b200 import ops
+    b, n, heads, dh = 2, 16, 8, 64
+    q = torch.randn(b, n, heads * dh, device='cuda')
+    kv = torch.randn(b, n, 2 * dh, device='cuda')
+    null_kv = torch.randn(2, dh, device='cuda')
+    ckv = torch.randn(b, nc, 2 * dh, device='cuda') if nc else None
+    out = ops.mq_attention(q, kv, null_kv, ckv, heads, dh)
+    qd = q.double().view(b, n, heads, dh).transpose(1, 2) * dh ** -0.5
+    k, v = kv.double().chunk(2, dim=-1)
+    k = torch.cat((null_kv[0].double().expand(b, 1, dh), k), dim=1)
+    v = torch.cat((null_kv[1].double().expand(b, 1, dh), v), dim=1)
+    if nc:
+        ck, cv = ckv.double().chunk(2, dim=-1)
+        k, v = torch.cat((ck, k), dim=1), torch.cat((cv, v), dim=1)
+    attn = torch.einsum('bhid,bjd->bhij', qd, k).softmax(dim=-1)
+    ref = torch.einsum('bhij,bjd->bhid', attn, v).transpose(1, 2).reshape(b, n, heads * dh).float()
+    _close(out, ref, TF32, 2e-5)
+
+
+def test_cross_attention():
+    from sparsefusion_b200 import ops
+    b, n, heads, dh, nc = 2, 16, 8, 64, 2
+    inner = heads * dh
+    q = torch.randn(b, n, inner, device='cuda')
+    kvc = torch.randn(b, nc, 2 * inner, device='cuda')
+    null_kv = torch.randn(2, dh, device='cuda')
+    out = ops.cross_attention(q, kvc, null_kv, heads, dh)
+    qd = q.double().view(b, n, heads, dh).transpose(1, 2) * dh ** -0.5
+    k, v = kvc.double().chunk(2, dim=-1)
+    k = k.view(b, nc, heads, dh).transpose(1, 2)
+    v = v.view(b, nc, heads, dh).transpose(1, 2)
+    k = torch.cat((null_kv[0].double().expand(b, heads, 1, dh), k), dim=2)
+    v = torch.cat((null_kv[1].double().expand(b, heads, 1, dh), v), dim=2)
+    attn = torch.einsum('bhid,bhjd->bhij', qd, k).softmax(dim=-1)
+    ref = torch.einsum('bhij,bhjd->bhid', attn, v).transpose(1, 2).reshape(b, n, inner).float()
+    _close(out, ref, TF32, 2e-5)
+
+
+def test_gca_pool_and_gate_residual():
+    from sparsefusion_b200 import ops
+    nb, h, w, c = 2, 16, 16, 256
+    x = torch.randn(nb, h, w, c, device='cuda')
+    wk, bk = torch.randn(1, c, 1, 1, device='cuda') / 16, torch.randn(1, device='cuda')
+    pooled = ops.gca_pool(x, wk, bk)
+    xd = x.double().view(nb, h * w, c)
+    logits = xd @ wk.double().view(c) + bk.double()
+    ref = torch.einsum('bp,bpc->bc', logits.softmax(dim=-1), xd).float()
+    _close(pooled, ref, 1e-4, 1e-5)
+    gate = torch.rand(nb, c, device='cuda')
+    res = torch.randn(nb, h, w, c, device='cuda')
+    _close(ops.gate_residual(x, gate, res), x * gate[:, None, None, :] + res, 1e-6, 1e-6)
+    _close(ops.gate_residual(x, None, res), x + res, 1e-6, 1e-6)

@@ -1,0 +1,84 @@
+"""Per-kernel timings on the GPU box (CUDA events, L2 flushed between iterations) -> gpurun_out/microbench.json.
+Used to pick tile/split heuristics and to fill DESIGN.md's per-kernel roofline table; not the headline bench."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sparsefusion_b200 import ops  # noqa: E402
+
+FLUSH = None
+
+
+def timeit(fn, iters=10, warmup=3, flush=True):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            FLUSH.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def conv_cases():
+    # (name, NB scale, H, Cin, Cout, K, stride)
+    base = [('init3', 32, 260, 128, 3, 1), ('init7', 32, 260, 64, 7, 1), ('init15', 32, 260, 64, 15, 1), ('d0.conv3', 32, 256, 256, 3, 1),
+            ('d0.down4s2', 32, 256, 256, 4, 2), ('d1.conv3', 16, 256, 256, 3, 1), ('d2.conv3', 8, 512, 512, 3, 1),
+            ('d3.conv3', 4, 1024, 1024, 3, 1), ('u0.conv3', 4, 2048, 1024, 3, 1), ('u0.res1x1', 4, 2048, 1024, 1, 1),
+            ('u1.conv3', 8, 1536, 1024, 3, 1), ('u2.conv3', 16, 768, 512, 3, 1), ('u3.conv3', 32, 512, 256, 3, 1),
+            ('ff1x1', 4, 1024, 2048, 1, 1), ('ps1x1', 4, 1024, 4096, 1, 1), ('final', 32, 256, 4, 3, 1)]
+    return base
+
+
+def main():
+    out = {'device': torch.cuda.get_device_name(0), 'conv': [], 'grid': {}}
+    for nb in (1, 8):
+        for name, h, cin, cout, k, stride in conv_cases():
+            x = ops.round_tf32(torch.randn(nb, h, h, cin, device='cuda'))
+            w = ops.pack_conv_weight(torch.randn(cout, cin, k, k, device='cuda') / (cin * k * k) ** 0.5)
+            b = torch.zeros(cout, device='cuda')
+            pad = (k - 1) // 2 if stride == 1 else 1
+            y = ops.conv2d_nhwc(x, w, cout, k, k, stride, pad, bias=b)
+            ms = timeit(lambda: ops.conv2d_nhwc(x, w, cout, k, k, stride, pad, bias=b, out=y))
+            ho = y.shape[1]
+            flops = 2.0 * nb * ho * ho * cout * cin * k * k
+            wbytes = w.numel() * 4
+            rec = dict(name=name, nb=nb, hw=h, cin=cin, cout=cout, k=k, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
+                       weight_gbs=round(wbytes / ms / 1e6, 1))
+            print(rec, flush=True)
+            out['conv'].append(rec)
+    # grid encoder operators at the render's sizes
+    from sparsefusion_b200.gridencoder import GridEncoder
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=8192, gridtype='tiled').cuda()
+    enc.embeddings.data.uniform_(-0.5, 0.5)
+    for B in (1 << 20, 1 << 21):
+        x = (torch.rand(B, 3, device='cuda') * 2 - 1) * 4
+        ms_f = timeit(lambda: enc(x, bound=4).sum() if False else enc(x, bound=4))
+        y = enc(x, bound=4)
+        g = torch.randn_like(y)
+        def fb():
+            enc.embeddings.grad = None
+            y2 = enc(x, bound=4)
+            y2.backward(g)
+        ms_fb = timeit(fb)
+        out['grid'][str(B)] = dict(fwd_ms=round(ms_f, 4), fwd_bwd_ms=round(ms_fb, 4), fwd_GBps_alg=round(B * 140 / ms_f / 1e6, 1))
+        print('grid', B, out['grid'][str(B)], flush=True)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
