@@ -36,6 +36,12 @@ extern "C" {
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
 int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Tensor-core operand precision of the UNet GEMMs.  1 (default) = error-compensated 3xTF32: operands stay fp32 in HBM, every
+ * stage is split hi/lo in shared memory and hi*hi + lo*hi + hi*lo is accumulated -- fp32-class accuracy, needed for the 1e-3
+ * contract on the predicted noise.  0 = single-pass TF32 (what the reference GPU build's cuDNN/cuBLAS did): operands are rounded
+ * to TF32 where they are produced; ~1.5e-3 relative error on the UNet output, ~1/3 of the tensor-pipe work. */
+int sfb_set_precision(int mode);
+int sfb_get_precision(void);
 
 /* ============================================================================================
  * 1. `_gridencoder` operator module      (external/gridencoder/src/bindings.cpp:5-8)
@@ -163,6 +169,51 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
 /* ResnetBlock tail (:727-729): out = h * gate[n][c] + res (gate NULL == 1) */
 int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const float* res, int64_t ldr, float* out, int64_t ldo, int NB,
                            int HW, int C, void* stream);
+
+/* ============================================================================================
+ * 4. Fused Instant-NGP field and optimiser   (external/nerf/network_grid.py NeRFNetwork, torch.optim.Adam)
+ * ========================================================================================== */
+
+/* NeRFNetwork.common_forward (network_grid.py:77-88) = GridEncoder (grid.py:138-154, the live tiled geometry: D=3, C=2, L=16)
+ * + MLP 32-64-64-4 (:14-33) + trunc_exp(h0 + density blob) (:69-75, ngp_activation.py:10-21) + sigmoid(h1:4), in ONE kernel.
+ * Points are either explicit (xyz [B,3], world coordinates in [-bound, bound]) or implicit ray samples: xyz == NULL and
+ * rays_o/rays_d [N,3], z [N*T] -> x = clamp(o + d*z, -bound, bound) exactly as renderer_df.py:367-368 computes it.
+ * W0 [64,32], W1 [64,64], W2 [4,64] are nn.Linear weights (row-major [out,in]).  sigma [B]; rgb [B,3] or NULL. */
+int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, uint32_t B,
+                          const float* embeddings, const int32_t* offsets, float S, uint32_t H, float bound, const float* W0,
+                          const float* b0, const float* W1, const float* b1, const float* W2, const float* b2, float* sigma, float* rgb,
+                          void* stream);
+/* Backward of the above w.r.t. every parameter (autograd through common_forward in the reference): grad_embeddings [rows,2]
+ * and gW*, gb* are ACCUMULATED into (caller zeroes them, like grid.py:72); grad_rgb may be NULL.  `tape` is scratch of
+ * sfb_ngp_field_tape_floats(B) floats (feature-major activation / pre-activation-gradient tapes for the weight gradients). */
+int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, uint32_t B,
+                           const float* embeddings, const int32_t* offsets, float S, uint32_t H, float bound, const float* W0,
+                           const float* b0, const float* W1, const float* b1, const float* W2, const float* b2, const float* grad_sigma,
+                           const float* grad_rgb, float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
+                           float* gb2, float* tape, void* stream);
+uint32_t sfb_ngp_field_tape_points(uint32_t B);
+uint64_t sfb_ngp_field_tape_floats(uint32_t B);
+/* The per-ray stages of NeRFRenderer.run (external/nerf/renderer_df.py:310-468; num_steps = upsample_steps = 64), one warp per ray.
+ * All random draws of the reference are inputs: noise [N,64] U(0,1) or NULL (perturb=False, :363); u [N,64] (torch.rand at :31, or the
+ * deterministic linspace of :28 in eval mode).  lin = torch.linspace(0,1,64) (:356), passed in so depths are bit-identical to torch's. */
+/* :328 near/far + :356-364 stratified depths -> nears [N], fars [N], z [N,64] */
+int sfb_ray_coarse_z(const float* rays_o, const float* rays_d, const float* aabb, float min_near, const float* lin, const float* noise,
+                     uint32_t N, uint32_t num_steps, float* nears, float* fars, float* z, void* stream);
+/* :381-395 (+ sample_pdf :15-49) + :404-405: coarse weights -> inverse-CDF samples -> merged, sorted depths z_sorted [N,128] */
+int sfb_ray_resample(const float* z_coarse, const float* sigma_coarse, const float* nears, const float* fars, const float* u, int det,
+                     uint32_t N, uint32_t num_steps, uint32_t upsample_steps, float* z_sorted, void* stream);
+/* :414-456: weights = alpha * cumprod(1 - alpha + 1e-15); image [N,3] (+ (1-ws)*bg_color), depth [N], weights_sum [N] */
+int sfb_ray_composite_forward(const float* z_sorted, const float* sigma, const float* rgb, const float* nears, const float* fars,
+                              float bg_color, uint32_t N, uint32_t T, float* image, float* depth, float* weights_sum, void* stream);
+/* what autograd derives for :414-456: grad_sigma [N,128], grad_rgb [N,128,3] from grad_image [N,3], grad_weights_sum / grad_depth [N] or NULL */
+int sfb_ray_composite_backward(const float* z_sorted, const float* sigma, const float* rgb, const float* nears, const float* fars,
+                               float bg_color, uint32_t N, uint32_t T, const float* grad_image, const float* grad_weights_sum,
+                               const float* grad_depth, float* grad_sigma, float* grad_rgb, void* stream);
+
+/* torch.optim.Adam.step for one parameter tensor (sparsefusion/distillation.py:165,246,352): no weight decay / amsgrad.
+ * grad is multiplied by grad_scale first (1/world_size after a sum all-reduce). step >= 1 is the step count after increment. */
+int sfb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

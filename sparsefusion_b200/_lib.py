@@ -34,7 +34,7 @@ def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[str, List[str]]]:
     text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
     text = re.sub(r'//[^\n]*', ' ', text)
     protos = {}
-    for m in re.finditer(r'\b(const\s+char\s*\*|int|void)\s+(sfb_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
+    for m in re.finditer(r'\b(const\s+char\s*\*|int|void|uint32_t|uint64_t|int64_t)\s+(sfb_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         args = [a.strip() for a in re.sub(r'\s+', ' ', args).split(',')]
         if args == ['void'] or args == ['']:
@@ -66,7 +66,8 @@ def load() -> ctypes.CDLL:
     for name, (ret, args) in _protos.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         fn.argtypes = [_argtype(a) for a in args]
-        fn.restype = ctypes.c_char_p if 'char' in ret else (None if ret == 'void' else ctypes.c_int)
+        fn.restype = {'void': None, 'int': ctypes.c_int, 'uint32_t': ctypes.c_uint32, 'uint64_t': ctypes.c_uint64,
+                      'int64_t': ctypes.c_int64}.get(ret, ctypes.c_char_p if 'char' in ret else ctypes.c_int)
     if lib.sfb_abi_version() != 1:
         raise RuntimeError('libsparsefusion_b200.so ABI version mismatch')
     _lib = lib

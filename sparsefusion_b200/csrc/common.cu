@@ -26,6 +26,10 @@ int check_launch(const char* what) {
     return SFB_OK;
 }
 
+static int g_precision = 1;  // 0: single-pass TF32 (operands rounded on write); 1: error-compensated 3xTF32 (default)
+int precision_mode() { return g_precision; }
+void set_precision_mode(int m) { g_precision = m; }
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -44,6 +48,13 @@ extern "C" {
 const char* sfb_last_error(void) { return sfb::last_error().c_str(); }
 
 int sfb_abi_version(void) { return SFB_ABI_VERSION; }
+
+int sfb_set_precision(int mode) {
+    if (mode != 0 && mode != 1) return sfb::fail(SFB_ERR_ARG, "set_precision: mode must be 0 (tf32) or 1 (tf32x3)");
+    sfb::set_precision_mode(mode);
+    return SFB_OK;
+}
+int sfb_get_precision(void) { return sfb::precision_mode(); }
 
 int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

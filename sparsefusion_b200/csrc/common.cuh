@@ -20,6 +20,10 @@ static inline __host__ __device__ T ceil_div(T a, T b) { return (a + b - 1) / b;
 
 int check_launch(const char* what);
 
+// tensor-core operand precision of the UNet GEMMs: 0 = TF32 single pass, 1 = 3xTF32 (error compensated)
+int precision_mode();
+void set_precision_mode(int m);
+
 // number of SMs of the current device (cached)
 int sm_count();
 

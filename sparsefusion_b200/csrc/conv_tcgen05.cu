@@ -49,25 +49,30 @@ struct alignas(64) ConvGemmParams {
     int32_t accumulate;
 };
 
-template <int BN>
+// NP = 1: single-pass TF32 (operands are expected TF32-rounded).  NP = 3: error-compensated "3xTF32": the epilogue
+// warps split every landed stage into hi (= what the tensor core keeps of the raw fp32 word) and lo = x - hi in shared
+// memory, and the issuer runs hi*hi + lo*hi + hi*lo, which restores ~fp32 accuracy (rel. error ~2^-21 per product).
+template <int BN, int NP>
 struct ConvCfg {
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int kRawBytes = kABytes + kBBytes;          // what TMA delivers per stage
+    static constexpr int kStageBytes = kRawBytes * (NP == 3 ? 2 : 1);
+    static constexpr int kStages = NP == 3 ? ((BN >= 256) ? 2 : (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5)))
+                                           : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers, bias*/ + BN * 4;
 };
 
-template <int BN>
+template <int BN, int NP>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, NP>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smemA = smem;
-    uint8_t* smemB = smem + S * kABytes;
+    // stage s: [A raw 16 KB | B raw BN*128 B | (NP == 3) A lo | B lo]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + S;
-    uint64_t* tmem_full_bar = empty_bar + S;
+    uint64_t* split_bar = empty_bar + S;
+    uint64_t* tmem_full_bar = split_bar + S;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* bias_s = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 512);
 
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
     const int niter = ke - kb;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); tc::mbar_init(&split_bar[i], 4); }
         tc::mbar_init(tmem_full_bar, 1);
         tc::fence_mbar_init();
     }
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                tc::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                tc::mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
                 const int i = kb + it;
                 const int tap = i / p.cin_chunks, cc = i - tap * p.cin_chunks;
                 const int ky = tap / p.KW, kx = tap - ky * p.KW;
@@ -115,8 +120,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
                     oy = (oy - py) >> 1;
                     ox = (ox - px) >> 1;
                 }
-                tc::tma_load_4d(smemA + s * kABytes, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
-                tc::tma_load_2d(smemB + s * Cfg::kBBytes, &p.tmB, &full_bar[s], i * kBK, cout0);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                tc::tma_load_4d(st, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
+                tc::tma_load_2d(st + kABytes, &p.tmB, &full_bar[s], i * kBK, cout0);
             }
         }
     } else if (warp == 1) {
@@ -126,13 +132,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
             for (int it = 0; it < niter; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
-                tc::mbar_wait(&full_bar[s], ph);
+                tc::mbar_wait(NP == 3 ? &split_bar[s] : &full_bar[s], ph);
                 tc::fence_after_sync();
-                const uint32_t a0 = tc::smem_u32(smemA + s * kABytes), b0 = tc::smem_u32(smemB + s * Cfg::kBBytes);
+                const uint32_t a0 = tc::smem_u32(smem + s * Cfg::kStageBytes), b0 = a0 + kABytes;
 #pragma unroll
                 for (int k = 0; k < kBK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                    tc::umma_tf32(tmem_base, tc::umma_desc_k_sw128(a0 + k * 32), tc::umma_desc_k_sw128(b0 + k * 32), idesc,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+                    const uint64_t da = tc::umma_desc_k_sw128(a0 + k * 32), db = tc::umma_desc_k_sw128(b0 + k * 32);
+                    tc::umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    if (NP == 3) {
+                        const uint64_t dal = tc::umma_desc_k_sw128(a0 + Cfg::kRawBytes + k * 32);
+                        const uint64_t dbl = tc::umma_desc_k_sw128(b0 + Cfg::kRawBytes + k * 32);
+                        tc::umma_tf32(tmem_base, dal, db, idesc, 1u);
+                        tc::umma_tf32(tmem_base, da, dbl, idesc, 1u);
+                    }
                 }
                 tc::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have read it
             }
@@ -146,6 +158,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
             bias_s[i] = (p.bias != nullptr && blockIdx.z == 0 && c < p.Cout) ? p.bias[c] : 0.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        if (NP == 3) {
+            // hi/lo split of every landed stage (same byte offsets => the swizzled layout is preserved)
+            constexpr int kVec = Cfg::kRawBytes / 16;
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                tc::mbar_wait(&full_bar[s], ph);
+                float4* raw = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes);
+                float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
+#pragma unroll 4
+                for (int i = et; i < kVec; i += 128) {
+                    const float4 v = raw[i];
+                    // hi is written back explicitly (exact TF32 bit patterns), so the result does not depend on how the
+                    // tensor core would have reduced a full fp32 word (truncation vs rounding)
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    raw[i] = h;
+                    lo[i] = l;
+                }
+                tc::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&split_bar[s]);
+            }
+        }
 
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;       // row of the tile == output pixel
@@ -263,14 +303,14 @@ static int make_map(CUtensorMap* out, const void* base, const uint64_t dims[4], 
     return SFB_OK;
 }
 
-template <int BN>
+template <int BN, int NP>
 static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::kSmemBytes));
+        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NP>::kSmemBytes));
         configured = true;
     }
-    conv_gemm_tf32_kernel<BN><<<grid, kThreads, ConvCfg<BN>::kSmemBytes, st>>>(p);
+    conv_gemm_tf32_kernel<BN, NP><<<grid, kThreads, ConvCfg<BN, NP>::kSmemBytes, st>>>(p);
     return check_launch("conv2d_nhwc_tf32");
 }
 
@@ -380,11 +420,19 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
         SFB_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)Cout * 4, (size_t)NB * Ho * Wo, st));
     }
     dim3 grid(tiles_m, tiles_c, splits);
+    if (precision_mode() == 1) {
+        switch (BN) {
+            case 32: return launch_conv<32, 3>(p, grid, st);
+            case 64: return launch_conv<64, 3>(p, grid, st);
+            case 128: return launch_conv<128, 3>(p, grid, st);
+            default: return launch_conv<256, 3>(p, grid, st);
+        }
+    }
     switch (BN) {
-        case 32: return launch_conv<32>(p, grid, st);
-        case 64: return launch_conv<64>(p, grid, st);
-        case 128: return launch_conv<128>(p, grid, st);
-        default: return launch_conv<256>(p, grid, st);
+        case 32: return launch_conv<32, 1>(p, grid, st);
+        case 64: return launch_conv<64, 1>(p, grid, st);
+        case 128: return launch_conv<128, 1>(p, grid, st);
+        default: return launch_conv<256, 1>(p, grid, st);
     }
 }
 }

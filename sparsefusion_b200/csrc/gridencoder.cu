@@ -236,9 +236,9 @@ extern "C" {
 int sfb_grid_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs, uint32_t B,
                             uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float* dy_dx, uint32_t gridtype,
                             int align_corners, void* stream) {
+    if (B == 0 || L == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(inputs && embeddings && offsets && outputs, "grid_encode_forward: null pointer");
     SFB_REQUIRE(gridtype <= 1, "grid_encode_forward: gridtype must be 0 (hash) or 1 (tiled)");
-    if (B == 0 || L == 0) return SFB_OK;
     return SFB_DISPATCH_DC(D, C, launch_forward, inputs, embeddings, offsets, outputs, B, L, S, H, dy_dx, gridtype, align_corners != 0,
                            as_stream(stream));
 }
@@ -246,10 +246,10 @@ int sfb_grid_encode_forward(const float* inputs, const float* embeddings, const 
 int sfb_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int32_t* offsets,
                              float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                              const float* dy_dx, float* grad_inputs, uint32_t gridtype, int align_corners, void* stream) {
+    if (B == 0 || L == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     (void)embeddings;
     SFB_REQUIRE(grad && inputs && offsets && grad_embeddings, "grid_encode_backward: null pointer");
     SFB_REQUIRE(gridtype <= 1, "grid_encode_backward: gridtype must be 0 (hash) or 1 (tiled)");
-    if (B == 0 || L == 0) return SFB_OK;
     return SFB_DISPATCH_DC(D, C, launch_backward, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs, gridtype,
                            align_corners != 0, as_stream(stream));
 }
@@ -262,8 +262,8 @@ int sfb_grid_level_scales(uint32_t L, float S, uint32_t H, float* scales, void* 
 
 int sfb_grid_corner_rows(const float* inputs, const int32_t* offsets, int32_t* rows, uint32_t B, uint32_t D, uint32_t L, float S,
                          uint32_t H, uint32_t gridtype, int align_corners, void* stream) {
+    if (B == 0 || L == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(inputs && offsets && rows, "grid_corner_rows: null pointer");
-    if (B == 0 || L == 0) return SFB_OK;
     dim3 grid(ceil_div(B, 256u), L);
     cudaStream_t st = as_stream(stream);
     switch (D) {

@@ -1,0 +1,465 @@
+// ngp_field.cu -- the Instant-NGP field query of SparseFusion's NeRFNetwork, fused, for sm_100a:
+//     xyz -> tiled-grid encode (16 levels x 2) -> MLP 32-64-64-4 (ReLU) -> sigma = exp(h0 + blob(x)), albedo = sigmoid(h1:4)
+// (external/nerf/network_grid.py:69-88 common_forward; external/gridencoder/grid.py:138-154; ngp_activation.py:10-21).
+// The reference runs this as ~12 eager launches per call (kernel_grid + permute + 3 cuBLAS GEMMs + elementwise) and
+// calls it three times per render; here one kernel evaluates a point once, and one kernel pair back-propagates.
+//
+// fp32 SIMT by design (the 1e-3 RGB contract and bit-exact grid indexing rule out reduced precision here):
+//   * one thread per point; the 7.1 MB embedding table stays L2-resident, corners fetched as 8-byte float2;
+//   * MLP weights live in shared memory TRANSPOSED ([k][j]) so that one broadcast LDS.128 feeds 4 FMAs; the
+//     per-thread activation vector lives in a conflict-free shared-memory column (hs[k][tid]), so the k loop is a
+//     real loop (small code, no register-indexed arrays);
+//   * backward recomputes the forward (no activation tape through HBM for the data path), scatters grid gradients
+//     with red.global.add.v2.f32, and writes feature-major activation / pre-activation-gradient tapes that the
+//     weight-gradient kernel reduces with a register-tiled outer-product GEMM (one red per weight per CTA).
+// Points are addressed either explicitly (xyz [B,3]) or implicitly as rays: x = clamp(o + d*z, aabb) with separate
+// fp32 multiply and add, which is bit-identical to the reference's torch expression (renderer_df.py:367-368).
+#include "common.cuh"
+#include "gridencoder.cuh"
+#include "../../include/sparsefusion_b200.h"
+
+namespace sfb {
+
+constexpr int kL = 16, kC = 2, kIn = 32, kHid = 64, kOut = 4;
+constexpr int kFieldThreads = 128;
+
+struct FieldGeom {
+    float S;
+    uint32_t H;
+    float bound;
+};
+
+struct PointSource {  // either xyz != null, or rays (o, d, z) with T samples per ray
+    const float* xyz;
+    const float* rays_o;
+    const float* rays_d;
+    const float* z;
+    uint32_t T;
+    float aabb_lo[3], aabb_hi[3];
+};
+
+__device__ __forceinline__ void fetch_point(const PointSource& ps, uint32_t p, float (&x)[3]) {
+    if (ps.xyz) {
+        x[0] = ps.xyz[(size_t)p * 3]; x[1] = ps.xyz[(size_t)p * 3 + 1]; x[2] = ps.xyz[(size_t)p * 3 + 2];
+    } else {
+        const uint32_t ray = p / ps.T;
+        const float zz = ps.z[p];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = __fadd_rn(ps.rays_o[(size_t)ray * 3 + d], __fmul_rn(ps.rays_d[(size_t)ray * 3 + d], zz));
+            x[d] = fminf(fmaxf(v, ps.aabb_lo[d]), ps.aabb_hi[d]);
+        }
+    }
+}
+
+// encode one point: 16 levels x (8 corners, float2) -> hs[2*l + c][tid]
+__device__ __forceinline__ void encode_point(const float (&x)[3], const float* __restrict__ table, const int32_t* __restrict__ offsets,
+                                             const FieldGeom& g, float* __restrict__ hs, int tid) {
+    float u[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(__fadd_rn(x[d], g.bound), 2 * g.bound);  // grid.py:142
+    const bool oob = grid_out_of_range<3>(u);
+#pragma unroll 1
+    for (uint32_t level = 0; level < kL; ++level) {
+        float a0 = 0.f, a1 = 0.f;
+        if (!oob) {
+            const GridLevel lv = grid_level(level, g.S, g.H, offsets);
+            const float* grid = table + (size_t)lv.offset * kC;
+            float frac[3];
+            uint32_t cell[3];
+            grid_locate<3>(u, lv.scale, false, frac, cell);
+#pragma unroll
+            for (uint32_t corner = 0; corner < 8; ++corner) {
+                float w = 1.f;
+                uint32_t cl[3];
+#pragma unroll
+                for (uint32_t d = 0; d < 3; ++d) {
+                    if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; cl[d] = cell[d]; }
+                    else { w *= frac[d]; cl[d] = cell[d] + 1; }
+                }
+                const uint32_t row = grid_row<3>(1u, false, lv.rows, lv.resolution, cl);
+                const float2 v = __ldg(reinterpret_cast<const float2*>(grid) + row);
+                a0 += w * v.x;
+                a1 += w * v.y;
+            }
+        }
+        hs[(2 * level) * kFieldThreads + tid] = a0;
+        hs[(2 * level + 1) * kFieldThreads + tid] = a1;
+    }
+}
+
+// acc[j] = bias[j] + sum_k WT[k][j] * hs[k][tid]      (WT transposed weights in smem, K in {32, 64}, 64 outputs)
+template <int K>
+__device__ __forceinline__ void dense64(const float* __restrict__ WT, const float* __restrict__ bias, const float* __restrict__ hs, int tid,
+                                        float (&acc)[kHid]) {
+#pragma unroll
+    for (int j = 0; j < kHid; ++j) acc[j] = bias[j];
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float hk = hs[k * kFieldThreads + tid];
+        const float4* w = reinterpret_cast<const float4*>(WT + k * kHid);
+#pragma unroll
+        for (int j4 = 0; j4 < kHid / 4; ++j4) {
+            const float4 wv = w[j4];
+            acc[4 * j4 + 0] += wv.x * hk; acc[4 * j4 + 1] += wv.y * hk;
+            acc[4 * j4 + 2] += wv.z * hk; acc[4 * j4 + 3] += wv.w * hk;
+        }
+    }
+}
+
+struct FieldSmem {
+    float WT0[kIn * kHid];   // [k][j]
+    float WT1[kHid * kHid];  // [k][j]
+    float WT2[kHid * kOut];  // [k][j]
+    float b0[kHid], b1[kHid], b2[kOut];
+};
+
+__device__ __forceinline__ void load_weights_T(FieldSmem& s, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                                               const float* b2) {
+    for (int i = threadIdx.x; i < kHid * kIn; i += blockDim.x) { const int j = i / kIn, k = i - j * kIn; s.WT0[k * kHid + j] = W0[i]; }
+    for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x) { const int j = i / kHid, k = i - j * kHid; s.WT1[k * kHid + j] = W1[i]; }
+    for (int i = threadIdx.x; i < kOut * kHid; i += blockDim.x) { const int j = i / kHid, k = i - j * kHid; s.WT2[k * kOut + j] = W2[i]; }
+    for (int i = threadIdx.x; i < kHid; i += blockDim.x) { s.b0[i] = b0[i]; s.b1[i] = b1[i]; }
+    if (threadIdx.x < kOut) s.b2[threadIdx.x] = b2[threadIdx.x];
+}
+
+__device__ __forceinline__ float density_blob(const float (&x)[3]) {  // network_grid.py:69-75
+    const float d = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    return 5.f * expf(-d / 0.08f);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kFieldThreads) field_forward_kernel(PointSource ps, uint32_t B, const float* __restrict__ table,
+                                                                     const int32_t* __restrict__ offsets, FieldGeom g,
+                                                                     const float* __restrict__ W0, const float* __restrict__ b0,
+                                                                     const float* __restrict__ W1, const float* __restrict__ b1,
+                                                                     const float* __restrict__ W2, const float* __restrict__ b2,
+                                                                     float* __restrict__ sigma, float* __restrict__ rgb) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    FieldSmem& s = *reinterpret_cast<FieldSmem*>(smraw);
+    float* hs = reinterpret_cast<float*>(smraw + sizeof(FieldSmem));
+    load_weights_T(s, W0, b0, W1, b1, W2, b2);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (uint32_t base = blockIdx.x * kFieldThreads; base < B; base += gridDim.x * kFieldThreads) {
+        const uint32_t p = base + tid;
+        if (p >= B) continue;  // no block-level sync inside the loop
+        float x[3];
+        fetch_point(ps, p, x);
+        encode_point(x, table, offsets, g, hs, tid);
+        float acc[kHid];
+        dense64<kIn>(s.WT0, s.b0, hs, tid, acc);
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) hs[j * kFieldThreads + tid] = fmaxf(acc[j], 0.f);
+        dense64<kHid>(s.WT1, s.b1, hs, tid, acc);
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) hs[j * kFieldThreads + tid] = fmaxf(acc[j], 0.f);
+        float o0 = s.b2[0], o1 = s.b2[1], o2 = s.b2[2], o3 = s.b2[3];
+#pragma unroll 4
+        for (int k = 0; k < kHid; ++k) {
+            const float hk = hs[k * kFieldThreads + tid];
+            const float4 w = *reinterpret_cast<const float4*>(s.WT2 + k * kOut);
+            o0 += w.x * hk; o1 += w.y * hk; o2 += w.z * hk; o3 += w.w * hk;
+        }
+        sigma[p] = expf(o0 + density_blob(x));
+        if (rgb) {
+            rgb[(size_t)p * 3] = 1.f / (1.f + expf(-o1));
+            rgb[(size_t)p * 3 + 1] = 1.f / (1.f + expf(-o2));
+            rgb[(size_t)p * 3 + 2] = 1.f / (1.f + expf(-o3));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward (data path)
+// tapes (feature-major, Bp = padded point count): H0 [32][Bp], H1 [64][Bp], H2 [64][Bp], D1 [64][Bp], D2 [64][Bp], D3 [4][Bp]
+struct FieldSmemBwd {
+    FieldSmem f;  // the transposed weights serve both directions: d_in[k] = dot(WT[k][:], d_out[:])
+};
+
+// d_in[k] = sum_j WT[k][j] * dreg[j]  for k < K (K inputs, 64 outputs): one row of the transposed weights per k
+template <int K>
+__device__ __forceinline__ float backprop_row(const float* __restrict__ WT, int k, const float (&dreg)[kHid]) {
+    const float4* w = reinterpret_cast<const float4*>(WT + k * kHid);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < kHid / 4; ++j4) {
+        const float4 wv = w[j4];
+        a0 += wv.x * dreg[4 * j4 + 0]; a1 += wv.y * dreg[4 * j4 + 1]; a2 += wv.z * dreg[4 * j4 + 2]; a3 += wv.w * dreg[4 * j4 + 3];
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(kFieldThreads) field_backward_kernel(PointSource ps, uint32_t B, uint32_t Bp, const float* __restrict__ table,
+                                                                      const int32_t* __restrict__ offsets, FieldGeom g,
+                                                                      const float* __restrict__ W0, const float* __restrict__ b0,
+                                                                      const float* __restrict__ W1, const float* __restrict__ b1,
+                                                                      const float* __restrict__ W2, const float* __restrict__ b2,
+                                                                      const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
+                                                                      float* __restrict__ grad_table, float* __restrict__ H0,
+                                                                      float* __restrict__ H1, float* __restrict__ H2, float* __restrict__ D1,
+                                                                      float* __restrict__ D2, float* __restrict__ D3) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    FieldSmemBwd& s = *reinterpret_cast<FieldSmemBwd*>(smraw);
+    float* hs = reinterpret_cast<float*>(smraw + sizeof(FieldSmemBwd));  // [64][128] activations
+    float* ds = hs + kHid * kFieldThreads;                                // [64][128] pre-activation gradients
+    load_weights_T(s.f, W0, b0, W1, b1, W2, b2);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (uint32_t base = blockIdx.x * kFieldThreads; base < Bp; base += gridDim.x * kFieldThreads) {
+        const uint32_t p = base + tid;
+        if (p >= Bp) continue;
+        if (p >= B) {  // padding rows of the tapes contribute nothing
+            for (int k = 0; k < kIn; ++k) H0[(size_t)k * Bp + p] = 0.f;
+            for (int k = 0; k < kHid; ++k) { H1[(size_t)k * Bp + p] = 0.f; H2[(size_t)k * Bp + p] = 0.f; D1[(size_t)k * Bp + p] = 0.f; D2[(size_t)k * Bp + p] = 0.f; }
+            for (int k = 0; k < kOut; ++k) D3[(size_t)k * Bp + p] = 0.f;
+            continue;
+        }
+        float x[3];
+        fetch_point(ps, p, x);
+        encode_point(x, table, offsets, g, hs, tid);
+#pragma unroll 4
+        for (int k = 0; k < kIn; ++k) H0[(size_t)k * Bp + p] = hs[k * kFieldThreads + tid];
+        float acc[kHid];
+        uint64_t mask1 = 0, mask2 = 0;
+        dense64<kIn>(s.f.WT0, s.f.b0, hs, tid, acc);
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) {
+            const float a = fmaxf(acc[j], 0.f);
+            mask1 |= (uint64_t)(acc[j] > 0.f) << j;
+            hs[j * kFieldThreads + tid] = a;
+            H1[(size_t)j * Bp + p] = a;
+        }
+        dense64<kHid>(s.f.WT1, s.f.b1, hs, tid, acc);
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) {
+            const float a = fmaxf(acc[j], 0.f);
+            mask2 |= (uint64_t)(acc[j] > 0.f) << j;
+            hs[j * kFieldThreads + tid] = a;
+            H2[(size_t)j * Bp + p] = a;
+        }
+        float o[4] = {s.f.b2[0], s.f.b2[1], s.f.b2[2], s.f.b2[3]};
+#pragma unroll 4
+        for (int k = 0; k < kHid; ++k) {
+            const float hk = hs[k * kFieldThreads + tid];
+            const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
+            o[0] += w.x * hk; o[1] += w.y * hk; o[2] += w.z * hk; o[3] += w.w * hk;
+        }
+        // output activations: trunc_exp backward clamps the exponent to +-15 (ngp_activation.py:19-21)
+        float d3[4];
+        const float pre = o[0] + density_blob(x);
+        d3[0] = g_sigma[p] * expf(fminf(fmaxf(pre, -15.f), 15.f));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float sg = 1.f / (1.f + expf(-o[c + 1]));
+            d3[c + 1] = g_rgb ? g_rgb[(size_t)p * 3 + c] * sg * (1.f - sg) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) D3[(size_t)c * Bp + p] = d3[c];
+        // d2 = (W2^T d3) * relu'(a2)
+#pragma unroll 4
+        for (int k = 0; k < kHid; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
+            float v = w.x * d3[0] + w.y * d3[1] + w.z * d3[2] + w.w * d3[3];
+            v = ((mask2 >> k) & 1ull) ? v : 0.f;
+            ds[k * kFieldThreads + tid] = v;
+            D2[(size_t)k * Bp + p] = v;
+        }
+        // d1 = (W1^T d2) * relu'(a1)
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) acc[j] = ds[j * kFieldThreads + tid];  // d2 into registers
+#pragma unroll 1
+        for (int k = 0; k < kHid; ++k) {
+            float v = backprop_row<kHid>(s.f.WT1, k, acc);
+            v = ((mask1 >> k) & 1ull) ? v : 0.f;
+            ds[k * kFieldThreads + tid] = v;  // own column; d2 is already in registers
+            D1[(size_t)k * Bp + p] = v;
+        }
+        // d0[k] = sum_j W0[j][k] d1[j]   (32 encoder features)
+#pragma unroll
+        for (int j = 0; j < kHid; ++j) acc[j] = ds[j * kFieldThreads + tid];  // d1 into registers
+        float d0[kIn];
+#pragma unroll
+        for (int k = 0; k < kIn; ++k) d0[k] = backprop_row<kIn>(s.f.WT0, k, acc);
+        // scatter into the embedding gradient (kernel_grid_backward, gridencoder.cu:226-313)
+        float u[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(__fadd_rn(x[d], g.bound), 2 * g.bound);
+        if (!grid_out_of_range<3>(u)) {
+#pragma unroll
+            for (uint32_t level = 0; level < kL; ++level) {
+                const GridLevel lv = grid_level(level, g.S, g.H, offsets);
+                float* gt = grad_table + (size_t)lv.offset * kC;
+                float frac[3];
+                uint32_t cell[3];
+                grid_locate<3>(u, lv.scale, false, frac, cell);
+                const float g0 = d0[2 * level], g1 = d0[2 * level + 1];
+#pragma unroll
+                for (uint32_t corner = 0; corner < 8; ++corner) {
+                    float w = 1.f;
+                    uint32_t cl[3];
+#pragma unroll
+                    for (uint32_t d = 0; d < 3; ++d) {
+                        if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; cl[d] = cell[d]; }
+                        else { w *= frac[d]; cl[d] = cell[d] + 1; }
+                    }
+                    const uint32_t row = grid_row<3>(1u, false, lv.rows, lv.resolution, cl);
+                    const float wg[2] = {w * g0, w * g1};
+                    grid_red_add_row<2>(gt, row, wg);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// dW[j][k] += sum_p D[j][p] * H[k][p];  db[j] += sum_p D[j][p].   D [J][Bp], H [K][Bp] feature-major.
+// CTA = 256 threads as a 16x16 grid of (J/16 x K/16) register tiles; points staged through smem 64 at a time.
+template <int J, int K>
+__global__ void __launch_bounds__(256) mlp_wgrad_kernel(const float* __restrict__ D, const float* __restrict__ H, uint32_t Bp,
+                                                       float* __restrict__ gW, float* __restrict__ gb) {
+    constexpr int TJ = (J + 15) / 16, TK = (K + 15) / 16, PT = 64;
+    __shared__ float Ds[J][PT + 1];
+    __shared__ float Hs[K][PT + 1];
+    const int tj = threadIdx.x / 16, tk = threadIdx.x % 16;
+    float acc[TJ][TK];
+    float accb[TJ];
+#pragma unroll
+    for (int a = 0; a < TJ; ++a) {
+        accb[a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < TK; ++b) acc[a][b] = 0.f;
+    }
+    const uint32_t chunks = Bp / PT;
+    for (uint32_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const uint32_t p0 = ch * PT;
+        for (int i = threadIdx.x; i < J * PT; i += 256) { const int j = i / PT, q = i % PT; Ds[j][q] = D[(size_t)j * Bp + p0 + q]; }
+        for (int i = threadIdx.x; i < K * PT; i += 256) { const int k = i / PT, q = i % PT; Hs[k][q] = H[(size_t)k * Bp + p0 + q]; }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = 0; q < PT; ++q) {
+            float dv[TJ], hv[TK];
+#pragma unroll
+            for (int a = 0; a < TJ; ++a) dv[a] = (tj * TJ + a < J) ? Ds[tj * TJ + a][q] : 0.f;
+#pragma unroll
+            for (int b = 0; b < TK; ++b) hv[b] = (tk * TK + b < K) ? Hs[tk * TK + b][q] : 0.f;
+#pragma unroll
+            for (int a = 0; a < TJ; ++a) {
+                if (tk == 0) accb[a] += dv[a];
+#pragma unroll
+                for (int b = 0; b < TK; ++b) acc[a][b] += dv[a] * hv[b];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < TJ; ++a) {
+        const int j = tj * TJ + a;
+        if (j >= J) continue;
+        if (tk == 0) atomicAdd(gb + j, accb[a]);
+#pragma unroll
+        for (int b = 0; b < TK; ++b) {
+            const int k = tk * TK + b;
+            if (k < K) atomicAdd(gW + (size_t)j * K + k, acc[a][b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam semantics (no amsgrad, no weight decay): one fused pass over a parameter group
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+static int field_args_ok(const float* table, const int32_t* offsets, const float* W0, const float* b0, const float* W1, const float* b1,
+                         const float* W2, const float* b2) {
+    return table && offsets && W0 && b0 && W1 && b1 && W2 && b2;
+}
+
+static PointSource make_source(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, float bound) {
+    PointSource ps;
+    ps.xyz = xyz; ps.rays_o = rays_o; ps.rays_d = rays_d; ps.z = z; ps.T = T ? T : 1;
+    for (int d = 0; d < 3; ++d) { ps.aabb_lo[d] = -bound; ps.aabb_hi[d] = bound; }
+    return ps;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, uint32_t B,
+                          const float* embeddings, const int32_t* offsets, float S, uint32_t H, float bound, const float* W0, const float* b0,
+                          const float* W1, const float* b1, const float* W2, const float* b2, float* sigma, float* rgb, void* stream) {
+    SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && sigma, "ngp_field_forward: null pointer");
+    SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_forward: give xyz or (rays_o, rays_d, z, T)");
+    if (B == 0) return SFB_OK;
+    const size_t smem = sizeof(FieldSmem) + (size_t)kHid * kFieldThreads * 4;
+    static bool cfg = false;
+    if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    const uint32_t blocks = min(ceil_div(B, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 3);
+    field_forward_kernel<<<blocks, kFieldThreads, smem, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
+                                                                            FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, sigma, rgb);
+    return check_launch("ngp_field_forward");
+}
+
+uint32_t sfb_ngp_field_tape_points(uint32_t B) { return (B + 63) / 64 * 64; }
+
+int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, uint32_t B,
+                           const float* embeddings, const int32_t* offsets, float S, uint32_t H, float bound, const float* W0, const float* b0,
+                           const float* W1, const float* b1, const float* W2, const float* b2, const float* grad_sigma, const float* grad_rgb,
+                           float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* tape,
+                           void* stream) {
+    SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && grad_sigma && grad_embeddings && gW0 && gb0 && gW1 && gb1 && gW2 &&
+                    gb2 && tape,
+                "ngp_field_backward: null pointer");
+    SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_backward: give xyz or (rays_o, rays_d, z, T)");
+    if (B == 0) return SFB_OK;
+    const uint32_t Bp = sfb_ngp_field_tape_points(B);
+    float* H0 = tape;
+    float* H1 = H0 + (size_t)kIn * Bp;
+    float* H2 = H1 + (size_t)kHid * Bp;
+    float* D1 = H2 + (size_t)kHid * Bp;
+    float* D2 = D1 + (size_t)kHid * Bp;
+    float* D3 = D2 + (size_t)kHid * Bp;
+    const size_t smem = sizeof(FieldSmemBwd) + (size_t)2 * kHid * kFieldThreads * 4;
+    static bool cfg = false;
+    if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    cudaStream_t st = as_stream(stream);
+    const uint32_t blocks = min(ceil_div(Bp, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 2);
+    field_backward_kernel<<<blocks, kFieldThreads, smem, st>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, Bp, embeddings, offsets,
+                                                              FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, grad_sigma, grad_rgb,
+                                                              grad_embeddings, H0, H1, H2, D1, D2, D3);
+    if (int rc = check_launch("ngp_field_backward(data)")) return rc;
+    const uint32_t wb = min(Bp / 64, (uint32_t)sm_count() * 2);
+    mlp_wgrad_kernel<kHid, kIn><<<wb, 256, 0, st>>>(D1, H0, Bp, gW0, gb0);
+    mlp_wgrad_kernel<kHid, kHid><<<wb, 256, 0, st>>>(D2, H1, Bp, gW1, gb1);
+    mlp_wgrad_kernel<kOut, kHid><<<wb, 256, 0, st>>>(D3, H2, Bp, gW2, gb2);
+    return check_launch("ngp_field_backward(weights)");
+}
+
+uint64_t sfb_ngp_field_tape_floats(uint32_t B) {
+    return (uint64_t)sfb_ngp_field_tape_points(B) * (kIn + 4 * kHid + kOut);
+}
+
+int sfb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                  int step, float grad_scale, void* stream) {
+    SFB_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "adam_step: null pointer or step < 1");
+    if (n == 0) return SFB_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
+    return check_launch("adam_step");
+}
+}

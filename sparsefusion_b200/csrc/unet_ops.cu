@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
 // y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ), rounded to tf32.  film [NB, 2C] (scale | shift) or null
 __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const float2* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
-                                int G, int act, int64_t total4) {
+                                int G, int act, int round, int64_t total4) {
     const int C4 = C >> 2, Cg = C / G;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = i / C4;
@@ -171,8 +171,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const 
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
         }
-        *reinterpret_cast<float4*>(y + pix * ldy + c) =
-            make_float4(tc::round_tf32(o[0]), tc::round_tf32(o[1]), tc::round_tf32(o[2]), tc::round_tf32(o[3]));
+        if (round) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = tc::round_tf32(o[k]);
+        }
+        *reinterpret_cast<float4*>(y + pix * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -289,7 +292,7 @@ __global__ void time_fourier_kernel(const float* __restrict__ t, const float* __
 // heads, null_kv [2,dh], optional context kv ckv [B,nc,2*dh].  Key order: context, null, tokens (:523-532).  out [B,n,heads*dh].
 // One warp per (b, head, query); dh <= 128.
 __global__ void mq_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ null_kv,
-                                    const float* __restrict__ ckv, float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale) {
+                                    const float* __restrict__ ckv, float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale, int round) {
     extern __shared__ float sm[];  // per warp: scores[nk]
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * warps + warp;
@@ -320,14 +323,14 @@ __global__ void mq_attention_kernel(const float* __restrict__ q, const float* __
     for (int e = lane; e < dh; e += 32) {
         float acc = 0.f;
         for (int j = 0; j < nk; ++j) acc += __expf(sc[j] - mx) * inv * key_ptr(j, 1)[e];
-        orow[e] = tc::round_tf32(acc);
+        orow[e] = round ? tc::round_tf32(acc) : acc;
     }
 }
 
 // Cross attention (imagen_pytorch.py:764-805): q [B,n,heads*dh]; kvc [B,nc,2*heads*dh] = (k | v) per context token, per-head slices;
 // null_kv [2,dh] shared by heads; keys: null, context.  One warp per (b, head, query).
 __global__ void cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const float* __restrict__ null_kv,
-                                       float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale) {
+                                       float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale, int round) {
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * warps + warp;
     if (gw >= B * heads * n) return;
@@ -354,7 +357,7 @@ __global__ void cross_attention_kernel(const float* __restrict__ q, const float*
             const float* vr = (j == 0) ? null_kv + dh : kvc + ((int64_t)(b * nc + (j - 1))) * 2 * inner + inner + h * dh;
             acc += scv[j] * inv * vr[e];
         }
-        orow[e] = tc::round_tf32(acc);
+        orow[e] = round ? tc::round_tf32(acc) : acc;
     }
 }
 
@@ -439,7 +442,7 @@ extern "C" {
 int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream) {
     SFB_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld, c_off, round_tf32);
+    nchw_to_nhwc_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
     return check_launch("nchw_to_nhwc");
 }
 
@@ -477,14 +480,14 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t total4 = (int64_t)NB * HW * (C / 4);
     gn_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
-                                                      act_silu, total4);
+                                                      act_silu, precision_mode() == 0, total4);
     return check_launch("groupnorm_nhwc(apply)");
 }
 
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
                        int C, int pre_gelu, int round_tf32, void* stream) {
     SFB_REQUIRE(x && g && y, "layernorm_rows: null pointer");
-    layernorm_rows_kernel<<<ceil_div(T, 8), 256, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32);
+    layernorm_rows_kernel<<<ceil_div(T, 8), 256, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
     return check_launch("layernorm_rows");
 }
 
@@ -497,13 +500,13 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
         const size_t sm = (size_t)2 * K * 4;
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)); cfg = true; }
-        linear_small_kernel<2><<<dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32);
+        linear_small_kernel<2><<<dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     } else {
         const size_t sm = (size_t)8 * K * 4;
         SFB_REQUIRE(sm <= 200 * 1024, "linear_small: K too large for 8-row tile");
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-        linear_small_kernel<8><<<dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32);
+        linear_small_kernel<8><<<dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     }
     return check_launch("linear_small");
 }
@@ -522,7 +525,7 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
     const int warps = 4;
     const size_t sm = (size_t)warps * nk * 4;
     SFB_REQUIRE(sm <= 48 * 1024, "mq_attention: too many keys for the single-pass kernel");
-    mq_attention_kernel<<<ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream)>>>(q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale);
+    mq_attention_kernel<<<ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream)>>>(q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("mq_attention");
 }
 
@@ -530,7 +533,7 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
                         void* stream) {
     SFB_REQUIRE(q && kvc && null_kv && out, "cross_attention: null pointer");
     SFB_REQUIRE(nc <= 8, "cross_attention: at most 8 context tokens");
-    cross_attention_kernel<<<ceil_div(B * heads * n, 4), 128, 0, as_stream(stream)>>>(q, kvc, null_kv, out, B, n, heads, dh, nc, scale);
+    cross_attention_kernel<<<ceil_div(B * heads * n, 4), 128, 0, as_stream(stream)>>>(q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("cross_attention");
 }
 

@@ -14,6 +14,17 @@ import torch
 from . import _lib as lib
 
 
+# --------------------------------------------------------------------------------------------- precision
+def set_precision(mode: str) -> None:
+    """'tf32x3' (default; error-compensated, fp32-class accuracy) or 'tf32' (single pass, operands rounded on write).
+    Packed weights depend on the mode: call ``Unet.prepare()`` again after switching."""
+    lib.call('sfb_set_precision', {'tf32': 0, 'tf32x3': 1}[mode])
+
+
+def get_precision() -> str:
+    return ('tf32', 'tf32x3')[lib.load().sfb_get_precision()]
+
+
 # --------------------------------------------------------------------------------------------- helpers
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
     """round-to-nearest (ties away from zero) fp32 -> tf32 kept in fp32 storage (== cvt.rna.tf32.f32)"""
@@ -26,14 +37,16 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
 
 def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     """nn.Conv2d weight [Cout,Cin,KH,KW] (or nn.Linear weight [O,K]) -> [Cout, KH*KW*ceil32(Cin)]
-    tap-major / channel-minor, zero padded, TF32-rounded: the K-major B operand of the implicit GEMM."""
+    tap-major / channel-minor, zero padded: the K-major B operand of the implicit GEMM.  TF32-rounded in 'tf32' mode,
+    raw fp32 in 'tf32x3' mode (the kernel splits hi/lo itself)."""
     if w.dim() == 2:
         w = w[:, :, None, None]
     cout, cin, kh, kw = w.shape
     cin_pad = (cin + 31) // 32 * 32
     p = torch.zeros(cout, kh, kw, cin_pad, dtype=torch.float32, device=w.device)
     p[..., :cin] = w.detach().float().permute(0, 2, 3, 1)
-    return round_tf32(p.reshape(cout, kh * kw * cin_pad)).contiguous()
+    p = p.reshape(cout, kh * kw * cin_pad)
+    return (round_tf32(p) if get_precision() == 'tf32' else p).contiguous()
 
 
 def _nhwc_meta(t: torch.Tensor) -> Tuple[int, int, int, int, int]:

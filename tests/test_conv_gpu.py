@@ -1,15 +1,23 @@
-"""tcgen05 implicit-GEMM convolution (sfb_conv2d_nhwc_tf32) against a plain PyTorch fp32 reference.
+"""tcgen05 implicit-GEMM convolution (sfb_conv2d_nhwc_tf32) against a plain PyTorch reference (fp64 accumulate).
 
-Two tolerances, both written here:
-  * operands pre-rounded to TF32 on both sides -> only the fp32 accumulation order differs: rel L2 <= 2e-6;
-  * raw fp32 operands -> the kernel's only approximation is the TF32 operand precision (10-bit mantissa,
-    what the reference GPU build's cuDNN/cuBLAS used): rel L2 <= 1e-3.
+Tolerances, all written here:
+  * operands pre-rounded to TF32 on both sides -> only the fp32 accumulation order differs: rel L2 <= 2e-6 (both modes);
+  * raw fp32 operands, 'tf32x3' mode (default: hi/lo split, 3 MMAs) -> fp32-class: rel L2 <= 5e-6;
+  * raw fp32 operands, 'tf32' mode (single pass; what the reference GPU build's cuDNN/cuBLAS did) -> rel L2 <= 1e-3.
 """
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=['tf32x3', 'tf32'])
+def mode(request):
+    from sparsefusion_b200 import ops
+    ops.set_precision(request.param)
+    yield request.param
+    ops.set_precision('tf32x3')
 
 
 def _ref_conv(x_nhwc, w, b, stride, pad):
@@ -35,7 +43,7 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES)
-def test_conv_matches_fp32_reference(case):
+def test_conv_matches_fp32_reference(case, mode):
     from sparsefusion_b200 import ops
     nb, h, w, cin, cout, k, stride, pad = case
     g = torch.Generator(device='cuda').manual_seed(1234 + cin + cout + k)
@@ -52,12 +60,12 @@ def test_conv_matches_fp32_reference(case):
     y2 = ops.conv2d_nhwc(x, ops.pack_conv_weight(wt), cout, k, k, stride, pad, bias=b)
     ref2 = _ref_conv(x, wt, b, stride, pad)
     rel2 = ((y2 - ref2).norm() / ref2.norm()).item()
-    assert rel2 < 1e-3, f'{case}: raw operands rel {rel2:.3e}'
+    assert rel2 < (5e-6 if mode == 'tf32x3' else 1e-3), f'{case} [{mode}]: raw operands rel {rel2:.3e}'
 
 
 @pytest.mark.parametrize('bn', [32, 64, 128, 256])
 @pytest.mark.parametrize('splits', [1, 3, 0])
-def test_conv_tilings_agree(bn, splits):
+def test_conv_tilings_agree(bn, splits, mode):
     from sparsefusion_b200 import ops
     g = torch.Generator(device='cuda').manual_seed(7)
     x = ops.round_tf32(torch.randn(2, 16, 16, 96, device='cuda', generator=g))
@@ -69,7 +77,7 @@ def test_conv_tilings_agree(bn, splits):
     assert rel < 2e-6, f'bn={bn} splits={splits}: rel {rel:.3e}'
 
 
-def test_conv_epilogue_residual_accumulate_and_channel_slices():
+def test_conv_epilogue_residual_accumulate_and_channel_slices(mode):
     from sparsefusion_b200 import ops
     g = torch.Generator(device='cuda').manual_seed(9)
     wide_in = ops.round_tf32(torch.randn(2, 8, 8, 160, device='cuda', generator=g))

@@ -12,9 +12,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _ref(name):
+    import os
     from oracle import build_ref
-    if not build_ref.available():
-        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    if not os.path.exists(build_ref.so_path(name)):
+        pytest.skip(f'oracle/_ref/{name}.so not built (needs /root/reference at build time)')
     return build_ref.load_module(name)
 
 

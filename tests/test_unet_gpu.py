@@ -52,8 +52,19 @@ def test_small_unet_layer_by_layer_vs_oracle(golden_dir):
             report.append((k, _rel(d, v)))
     print('\n'.join(f'  {k:24s} rel {r:.3e}' for k, r in report))
     print(f'  eps rel vs oracle {_rel(eps, ref):.3e}; vs reference golden {_rel(eps, torch.from_numpy(g["eps"])):.3e}')
-    assert max(r for _, r in report) < 2e-3
+    assert max(r for _, r in report) < 1e-3
     assert _rel(eps, torch.from_numpy(g['eps'])) < 1e-3
+    # single-pass TF32 (the reference GPU build's arithmetic class) is available as an option; it misses the 1e-3 bar
+    from sparsefusion_b200 import ops
+    ops.set_precision('tf32')
+    try:
+        unet.prepare()
+        e1 = unet.forward(x.cuda(), log_snr.cuda(), cond_images=cond.cuda()).cpu()
+    finally:
+        ops.set_precision('tf32x3')
+        unet.prepare()
+    print(f'  single-pass tf32 eps rel vs reference golden {_rel(e1, torch.from_numpy(g["eps"])):.3e}')
+    assert _rel(e1, torch.from_numpy(g['eps'])) < 5e-3
 
 
 def test_full_unet_vs_reference_golden_and_fp64(golden_dir):

@@ -51,7 +51,10 @@ def test_groupnorm_film_silu(shape, film):
         ref = ref * (sc + 1) + sh
     ref = F.silu(ref).permute(0, 2, 3, 1).float()
     _close(y, ref, TF32, 2e-5)
-    assert ((y.view(torch.int32) & 0x1FFF) == 0).all(), 'GroupNorm output must be TF32-rounded'
+    if ops.get_precision() == 'tf32':
+        assert ((y.view(torch.int32) & 0x1FFF) == 0).all(), 'GroupNorm output must be TF32-rounded in single-pass mode'
+    else:
+        _close(y, ref, 2e-5, 2e-5)   # 3xTF32 mode keeps full fp32 activations
 
 
 def test_layernorm_variants():

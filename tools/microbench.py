@@ -43,8 +43,58 @@ def conv_cases():
     return base
 
 
+def unet_bench(out):
+    import numpy as np
+    from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
+    unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
+                layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
+    torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)
+    out['unet'] = {}
+    for mode in ('tf32x3', 'tf32'):
+        ops.set_precision(mode)
+        unet.prepare()
+        for nb in (1, 8):
+            x, cond, t = torch.randn(nb, 4, 32, 32, device='cuda'), torch.randn(nb, 256, 32, 32, device='cuda'), torch.full((nb,), 0.3, device='cuda')
+            eager = timeit(lambda: unet.forward(x, t, cond_images=cond), iters=5, warmup=2, flush=False)
+            runner = UnetGraph(unet)
+            graph = timeit(lambda: runner(x, t, cond), iters=20, warmup=3, flush=True)
+            rec = dict(eager_ms=round(eager, 3), graph_ms=round(graph, 3), tflops=round(62.83e-3 * nb / graph, 1), weight_gbs=round(1602.7 / graph, 1))
+            out['unet'][f'{mode}_nb{nb}'] = rec
+            print('unet', mode, nb, rec, flush=True)
+    ops.set_precision('tf32x3')
+
+
+def render_bench(out):
+    import numpy as np
+    from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
+    opt = get_default_torch_ngp_opt()
+    net = NeRFNetwork(opt).cuda().train()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    N = 128 * 128
+    o = torch.tensor([0.0, 1.3, 4.8], device='cuda').expand(N, 3).contiguous()
+    ys, xs = torch.meshgrid(torch.linspace(1, -1, 128, device='cuda'), torch.linspace(1, -1, 128, device='cuda'), indexing='ij')
+    d = torch.stack([xs / 4, ys / 4 - 0.27, -torch.ones_like(xs)], dim=-1).reshape(N, 3).contiguous()
+    kw = dict(staged=False, perturb=True, bg_color=0, ambient_ratio=1.0, shading='albedo', force_all_rays=True, **vars(opt))
+    def fwd():
+        with torch.no_grad():
+            net.render(o[None], d[None], **kw)
+    def fwd_bwd():
+        net.zero_grad(set_to_none=True)
+        r = net.render(o[None], d[None], **kw)
+        (r['image'].mean() + r['weights_sum'].mean()).backward()
+    out['render'] = dict(rays=N, fwd_ms=round(timeit(fwd, iters=10), 3), fwd_bwd_ms=round(timeit(fwd_bwd, iters=10), 3))
+    print('render', out['render'], flush=True)
+
+
 def main():
     out = {'device': torch.cuda.get_device_name(0), 'conv': [], 'grid': {}}
+    if 'unet' in sys.argv or len(sys.argv) == 1:
+        unet_bench(out)
+    if 'render' in sys.argv or len(sys.argv) == 1:
+        render_bench(out)
+    if len(sys.argv) > 1 and 'conv' not in sys.argv:
+        json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
+        return
     for nb in (1, 8):
         for name, h, cin, cout, k, stride in conv_cases():
             x = ops.round_tf32(torch.randn(nb, h, h, cin, device='cuda'))
