@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- SparseFusion score-distillation steps/sec on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one iteration of the reference's distillation loop in SDS mode (sparsefusion/distillation.py:174-352, itr > 1000):
+photometric sub-step on an input view + fusion sub-step on a cached target view (render 128x128 rays x (64+64) samples, bilinear x2,
+VAE encode, PLMS sampler with n+1 UNet evaluations, n = min(int(100*max_thres), 50), VAE decode, L1*(1-alpha_bar) loss, backward, Adam).
+Workload = BASELINE.json configs[2] (the configuration the metric is quoted on): 2 input views, 64 cached target views, 256^2 images,
+32x32x4 latents, synthetic hydrant-style cameras, random-init networks of the reference's architecture, synthetic data.
+With N GPUs every rank runs the step on its own target view (weak scaling over views) and the NGP gradients are all-reduced; `value`
+counts view-steps of all ranks per second.  The max_thres sequence is seeded, identical for every arm and rank.
+
+Printed JSON (rank 0): see the driver contract; `roofline` describes the dominant kernel (the tcgen05 conv/linear GEMM: it streams the
+UNet's 1.6 GB of fp32 weights once per evaluation), `cpu_baseline` the oracle port of the same step on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+UNET_KW = dict(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
+               layer_cross_attns=(False, False, False, False), cond_images_channels=256, attn_pool_text=False)
+DDPM_KW = dict(channels=4, conditional_encoder=None, conditional_embed_dim=None, image_sizes=(32,), timesteps=500, cond_drop_prob=0.1,
+               pred_objectives='noise', conditional=False, auto_normalize_img=False, clip_output=True, dynamic_thresholding=False,
+               dynamic_thresholding_percentile=.68, clip_value=10)
+UNET_WEIGHT_BYTES = 400_675_357 * 4          # algorithmic HBM bytes per UNet evaluation (fp32 weights, read once)
+UNET_FLOPS = 62.83e9                          # per sample at 32x32 latents
+WORKLOAD = ('sds_distillation_step: BASELINE configs[2] -- 2 input views, 64 cached target views, 256x256 images, 32x32x4 latents, '
+            '128x128 rays x (64+64) samples, PLMS(50), max_thres~U(0,0.99) seeded')
+
+
+def max_thres_sequence(n, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    return [float(torch.rand(1, generator=g).clamp(0.0, 0.99)) for _ in range(n)]
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.idx, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU arm
+def build_gpu(rank, world, device):
+    from sparsefusion_b200.distillation import Distiller, SceneCache
+    from sparsefusion_b200.imagen_pytorch import Unet
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
+    from sparsefusion_b200.synthetic import synthetic_scene
+    from sparsefusion_b200.vldm import DDPM
+    torch.manual_seed(0)          # identical random-init weights on every rank
+    torch.cuda.manual_seed(0)
+    unet = Unet(**UNET_KW)
+    torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)   # zero-init final conv would make eps == 0
+    ddpm = DDPM(unets=(unet,), **DDPM_KW)
+    torch.nn.init.normal_(ddpm.unets[0].get_parameter('final_conv.weight'), std=0.02)
+    ddpm = ddpm.to(device)
+    vae = AutoencoderKL().to(device).eval()
+    opt = get_default_torch_ngp_opt()
+    ngp = NeRFNetwork(opt)
+    ngp.encoder.embeddings.data.uniform_(-0.5, 0.5)                             # the default +-1e-4 is a featureless blob
+    ngp = ngp.to(device).train()
+    scene = SceneCache(**synthetic_scene(seed=0))
+    pg = torch.distributed.group.WORLD if world > 1 else None
+    return Distiller, dict(ngp=ngp, vae=vae, vldm=ddpm, opt=opt), scene, dict(seed=0, rank=rank, world_size=world, process_group=pg)
+
+
+def run_gpu(args):
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback for the product path)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=device)
+    torch.backends.cudnn.allow_tf32 = True       # VAE (not yet ported, torch): the arithmetic class of the reference GPU build
+    torch.backends.cuda.matmul.allow_tf32 = True
+    from sparsefusion_b200 import _lib, ops
+    _lib.load()
+    Distiller, nets, scene, kw = build_gpu(rank, world, device)
+    K, W = args.steps, args.warmup
+    thres = max_thres_sequence(2 * (K + W) + 8)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(dist, step_fn, n, offset):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step_fn(dist, 1001 + offset + i, thres[offset + i])
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- (1) device-resident: the scene cache lives in HBM before the timed region
+    dist = Distiller(cache=scene.to(device), **nets, **kw)
+    step_dev = lambda d, itr, mt: d.step(itr, max_thres=mt)
+    for i in range(W):
+        step_dev(dist, 1001 + i, thres[i])
+    clocks = ClockSampler(local)
+    l0 = ops.launch_count()
+    if rank == 0:
+        clocks.start()
+    if dist.sampler._graph is not None:
+        dist.sampler._graph.timing = []
+    n_calls = []
+    orig_step = step_dev
+
+    def step_counting(d, itr, mt):
+        orig_step(d, itr, mt)
+        n_calls.append(d.last.get('unet_calls', 0))
+    ms = timed(dist, step_counting, K, W)
+    clk = clocks.stop() if rank == 0 else None
+    launches = ops.launch_count() - l0
+    unet_events = dist.sampler._graph.timing if dist.sampler._graph is not None else []
+    unet_ms = sum(a.elapsed_time(b) for a, b in unet_events)
+    n_unet = len(unet_events)
+    if dist.sampler._graph is not None:
+        dist.sampler._graph.timing = None
+    value = world * K / (ms / 1e3)
+
+    # ---- (2) end to end through the public API with HOST buffers: pinned scene cache, per-step H2D of the step's views, D2H of the losses
+    e2e_val, h2d, d2h = None, 0, 0
+    if not args.no_e2e:
+        host = scene.pin()
+        dist.cache = None
+        bytes_per_step = [0]
+
+        def step_e2e(d, itr, mt):
+            g = d.gen.get_state()
+            n_in, n_t = host.input_rgb.shape[0], host.target_features.shape[0]
+            idx = int(torch.randperm(n_in, generator=d.gen)[0])
+            vi = int(torch.randperm(n_t, generator=d.gen)[(1 + d.rank) % n_t])
+            d.gen.set_state(g)    # the step itself redraws the same indices
+            d.cache = _StagedCache(host, device, idx, vi)   # this step's two views: pinned host -> HBM, inside the timed region
+            bytes_per_step[0] = d.cache.bytes
+            a, b = d.step(itr, max_thres=mt)
+            return float(a.item()) + float(b.item())   # D2H read of the step's losses (the reference logs loss.item(), :249,:349)
+        for i in range(2):
+            step_e2e(dist, 1001 + i, thres[i])
+        ms_e2e = timed(dist, step_e2e, K, W + K)
+        e2e_val, h2d, d2h = world * K / (ms_e2e / 1e3), bytes_per_step[0], 8
+
+    # ---- (3) roofline of the dominant kernel: instrumented eager UNet evaluations (CUDA events around every conv launch)
+    roof = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        unet = nets['vldm'].unets[0]
+        x = torch.randn(1, 4, 32, 32, device=device)
+        c = torch.randn(1, 256, 32, 32, device=device)
+        t = torch.full((1,), 0.3, device=device)
+        for _ in range(2):
+            unet.forward(x, t, cond_images=c)
+        torch.cuda.synchronize()
+        _lib.call('sfb_conv_prof_enable', 1)
+        reps = 5
+        for _ in range(reps):
+            unet.forward(x, t, cond_images=c)
+        import ctypes
+        tot, nl, wb, fl = ctypes.c_double(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        _lib.load().sfb_conv_prof_collect(ctypes.byref(tot), ctypes.byref(nl), ctypes.byref(wb), ctypes.byref(fl))
+        _lib.call('sfb_conv_prof_enable', 0)
+        conv_ms_per_eval = tot.value / reps
+        per_launch_us = 1e3 * tot.value / max(1, nl.value)
+        achieved = (wb.value / reps) / (conv_ms_per_eval * 1e-3) / 1e9
+        roof = {'kernel': 'conv_gemm_tf32_kernel (tcgen05 implicit-GEMM conv/linear)', 'bound': 'hbm', 'achieved': round(achieved, 1),
+                'peak': pk['hbm_gbs'], 'peak_source': f'{pk_kind} MEASURED_PEAKS.json hbm_gbs (copy bandwidth)', 'unit': 'GB/s',
+                'frac': round(achieved / pk['hbm_gbs'], 4), 'traffic': None,
+                'algorithmic_bytes_per_eval': int(wb.value / reps), 'launches_per_eval': nl.value // reps,
+                'avg_launch_us': round(per_launch_us, 2), 'conv_ms_per_unet_eval': round(conv_ms_per_eval, 4),
+                'tensor_tflops_equiv': round((fl.value / reps) / (conv_ms_per_eval * 1e-3) / 1e12, 2),
+                'unet_eval_ms_in_timed_region': round(unet_ms / max(1, n_unet), 4), 'unet_evals_in_timed_region': n_unet,
+                'unet_share_of_step': round(unet_ms / ms, 4),
+                'note': 'B=1 UNet evaluation is weight-streaming bound (SURVEY §7): achieved = fp32 weight bytes of the conv/linear layers '
+                        'per evaluation / summed conv-kernel time per evaluation (CUDA events around each launch, eager pass after the timed region)'}
+
+    # ---- (4) CPU baseline (oracle port) on the host cores, rank 0, N == 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(float(np.mean(n_calls)) if n_calls else 38.0)
+
+    if rank == 0:
+        out = {'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(value, 4), 'unit': 'steps/s', 'n_gpus': world,
+               'steps': K, 'warmup': W, 'ms_per_step': round(ms / K, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32 (UNet GEMMs: 3xTF32 error-compensated tensor-core passes, fp32 accumulate; NGP: fp32)', 'data': 'synthetic',
+               'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, 7.46 MB NGP-gradient all-reduce per sub-step',
+                          'unet_evals_per_step_mean': round(float(np.mean(n_calls)), 2) if n_calls else None,
+                          'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
+                          'vae': 'torch (cuDNN, TF32) -- SURVEY §8f next row, not yet ported', 'lpips': 'excluded in every arm (un-vendored dependency)',
+                          'precision_mode': ops.get_precision()},
+               'clocks': clk, 'gpu_launches': int(launches),
+               'e2e': None if e2e_val is None else {'value': round(e2e_val, 4), 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+               'roofline': roof, 'cpu_baseline': cpu}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+class _StagedCache:
+    """SceneCache view for the end-to-end leg: the step's two views are copied host(pinned) -> device when the step starts"""
+
+    def __init__(self, host, device, in_idx, tgt_idx):
+        self.bytes = 0
+
+        def stage(t, i):
+            d = t[i:i + 1].to(device, non_blocking=True)
+            self.bytes += d.numel() * d.element_size()
+            return _OneView(d, i, t.shape[0])
+        self.input_rgb, self.input_mask = stage(host.input_rgb, in_idx), stage(host.input_mask, in_idx)
+        self.input_rays_o, self.input_rays_d = stage(host.input_rays_o, in_idx), stage(host.input_rays_d, in_idx)
+        self.target_features = stage(host.target_features, tgt_idx)
+        self.target_rays_o, self.target_rays_d = stage(host.target_rays_o, tgt_idx), stage(host.target_rays_d, tgt_idx)
+        self.target_eft_image = _OneView(None, tgt_idx, host.target_eft_image.shape[0])   # not read in SDS mode
+
+
+class _OneView:
+    def __init__(self, data, index, n):
+        self.data, self.index, self.shape = data, index, (n,) + (tuple(data.shape[1:]) if data is not None else ())
+        self.device = data.device if data is not None else None
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            assert key.start == self.index, 'staged view mismatch'
+            return self.data
+        assert key == self.index, 'staged view mismatch'
+        return self.data[0]
+
+
+# ------------------------------------------------------------------------------------------------------------------ CPU arm
+class CpuPort:
+    """the oracle port of the step's components on all host cores (set up once, sampled per call)"""
+
+    def __init__(self, ray_sample=2048):
+        from oracle import ngp_oracle as no, unet_oracle as uo
+        from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+        torch.set_num_threads(os.cpu_count())
+        self.no, self.uo, self.cfg = no, uo, uo.FULL
+        self.sd = uo.make_params(self.cfg, seed=0)
+        self.x, self.c = torch.randn(1, 4, 32, 32), torch.randn(1, 256, 32, 32)
+        self.ls = uo.alpha_cosine_log_snr(torch.tensor([0.3]))
+        self.vae = AutoencoderKL().eval()
+        self.img = torch.rand(1, 3, 256, 256)
+        self.p = {k: v.clone().requires_grad_(True) for k, v in no.make_field_params(seed=0).items()}
+        ro, rd = no.camera_rays(no.circle_cameras(64)[3], 128, 128)
+        sel = np.random.default_rng(0).choice(ro.shape[0], ray_sample, replace=False)
+        self.ro, self.rd, self.ray_sample = torch.from_numpy(ro[sel]), torch.from_numpy(rd[sel]), ray_sample
+        with torch.no_grad():
+            uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c)   # warm-up
+
+    def sample(self, with_vae=True):
+        """(seconds per UNet evaluation, per VAE encode+decode, per full-size render fwd+bwd [scaled from the ray sample])"""
+        with torch.no_grad():
+            t0 = time.perf_counter(); self.uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c); t_unet = time.perf_counter() - t0
+        t_vae = None
+        if with_vae:
+            with torch.no_grad():
+                t0 = time.perf_counter(); z = self.vae.encode(self.img * 2 - 1).mode(); self.vae.decode(z); t_vae = time.perf_counter() - t0
+        for v in self.p.values():
+            v.grad = None
+        n = self.ray_sample
+        t0 = time.perf_counter()
+        r = self.no.run(self.no.Field(self.p), self.ro, self.rd, perturb_noise=torch.rand(n, 64), pdf_noise=torch.rand(n, 64))
+        (r['image'].mean() + r['weights_sum'].mean()).backward()
+        t_render = (time.perf_counter() - t0) * (128 * 128 / n)
+        return t_unet, t_vae, t_render
+
+
+def cpu_baseline(mean_calls):
+    t_unet, t_vae, t_render = CpuPort().sample()
+    step_s = 2 * t_render + mean_calls * t_unet + t_vae
+    return {'value': round(1.0 / step_s, 6), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': f'oracle port on {os.cpu_count()} host threads: 1 UNet evaluation ({t_unet:.3f} s), VAE encode+decode at 256^2 ({t_vae:.3f} s), '
+                      f'render fwd+bwd on 2048 of 16384 rays scaled x8 ({t_render:.3f} s); step = 2 renders + {mean_calls:.1f} UNet evals + VAE '
+                      f'(extrapolated, not run for a whole step). The reference has no CPU path for the NGP render (CUDA-only extensions).'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    thres = max_thres_sequence(2 * (K + W) + 8)
+    calls = [min(int(t * 100), 50) + 1 if t >= 0.01 else 0 for t in thres[W:W + K]]
+    per_step = []
+    port = CpuPort()
+    t_vae = None
+    t_begin = time.perf_counter()
+    for i in range(W + K):
+        t_unet, tv, t_render = port.sample(with_vae=(i < max(W, 1) + 1))   # the VAE cost is input independent: sampled during warm-up + once
+        if tv is not None:
+            t_vae = tv if t_vae is None else min(t_vae, tv)
+        if i >= W:
+            per_step.append(2 * t_render + calls[i - W] * t_unet + t_vae)
+        if time.perf_counter() - t_begin > 240 and len(per_step) >= 1:   # keep the whole run within a few minutes
+            break
+    step_s = float(np.mean(per_step))
+    val = 1.0 / step_s
+    out = {'impl': 'reference', 'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(val, 6), 'unit': 'steps/s',
+           'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': K, 'warmup': W, 'ms_per_step': round(step_s * 1e3, 1), 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': WORKLOAD, 'parallelism': 'host CPU, all cores', 'lpips': 'excluded in every arm'},
+           'cpu_baseline': {'value': round(val, 6), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                            'sample': f'{len(per_step)} bounded samples: per step 1 UNet evaluation + VAE enc/dec + render fwd/bwd on 2048/16384 rays, '
+                                      'scaled to the step (2 renders + n+1 UNet evals + VAE); oracle port (the reference cannot be imported on this box '
+                                      'and has no CPU render path)'},
+           'e2e': {'value': round(val, 6), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-e2e', dest='no_e2e', action='store_true')
+    ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_gpu(a)

@@ -42,6 +42,8 @@ int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * to TF32 where they are produced; ~1.5e-3 relative error on the UNet output, ~1/3 of the tensor-pipe work. */
 int sfb_set_precision(int mode);
 int sfb_get_precision(void);
+/* number of kernels this library has launched so far in this process (bench.py's "gpu_launches") */
+uint64_t sfb_launch_count(void);
 
 /* ============================================================================================
  * 1. `_gridencoder` operator module      (external/gridencoder/src/bindings.cpp:5-8)
@@ -133,6 +135,9 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
                          int stride, int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                          int accumulate, int splits, int bn, void* stream);
 int sfb_conv_weight_k(int Cin, int KH, int KW);
+/* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
+int sfb_conv_prof_enable(int on);
+int sfb_conv_prof_collect(double* total_ms, int* launches, double* weight_bytes, double* flops);
 /* experiment switch: encode activation/weight tensor maps as TFLOAT32 instead of FLOAT32 */
 int sfb_conv_set_tma_tf32(int enable);
 
@@ -145,9 +150,13 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 /* nn.SiLU + nn.PixelShuffle(2) of PixelShuffleUpsample (:588-592): y [NB,H,W,4*Co] -> out [NB,2H,2W,ldo] */
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
 /* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
- * stats_ws: NB*G*2 floats of workspace.  Output is TF32-rounded (it feeds the conv). */
+ * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch; counters: NB*G uint32 that are ZERO on entry (the
+ * kernel leaves them zero: the statistics are reduced slab-wise across CTAs and the last slab finalises).  Output is TF32-rounded in
+ * single-pass mode (it feeds the conv). */
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
-                       int64_t film_ld, int act_silu, float eps, float* stats_ws, float* y, int64_t ldy, void* stream);
+                       int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy,
+                       void* stream);
+int sfb_groupnorm_ws_floats(int NB, int G);
 /* LayerNorm / ChanLayerNorm (:301-329; gain g, optional bias b for nn.LayerNorm) over the last dim of [T,C] rows,
  * optionally of GELU(x) (ChanFeedForward :958-959), optionally + res (the `attn(x) + x` of :986) */
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
@@ -163,7 +172,7 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
                      int nc, float scale, void* stream);
 int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, float* out, int B, int n, int heads, int dh, int nc,
                         float scale, void* stream);
-/* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW floats */
+/* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW + 2*NB + 2 floats */
 int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
                  void* stream);
 /* ResnetBlock tail (:727-729): out = h * gate[n][c] + res (gate NULL == 1) */

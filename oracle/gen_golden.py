@@ -104,6 +104,25 @@ def gen_plms():
     np.savez_compressed(os.path.join(GOLD, 'plms_small.npz'), **out)
 
 
+def gen_vae():
+    """the plain-torch VAE mirror vs the reference's Encoder / Decoder (external/ldm/modules/diffusionmodules/model.py)"""
+    sys.path.insert(0, REF)
+    from external.ldm.modules.diffusionmodules.model import Encoder as REnc, Decoder as RDec
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2,
+              attn_resolutions=[], dropout=0.0)
+    torch.manual_seed(0)
+    renc, rdec = REnc(**dd).eval(), RDec(**dd).eval()
+    vae = AutoencoderKL().eval()
+    vae.encoder.load_state_dict(renc.state_dict(), strict=True)
+    vae.decoder.load_state_dict(rdec.state_dict(), strict=True)
+    x, z = torch.randn(1, 3, 64, 64), torch.randn(1, 4, 8, 8)
+    with torch.no_grad():
+        de, dd_ = (renc(x) - vae.encoder(x)).abs().max().item(), (rdec(z) - vae.decoder(z)).abs().max().item()
+    print(f'[vae] mirror vs reference Encoder/Decoder: max abs diff {de:.1e} / {dd_:.1e}')
+    assert de == 0.0 and dd_ == 0.0
+
+
 def gen_ngp():
     from oracle import ngp_oracle as no
     no.write_golden(GOLD)
@@ -111,7 +130,7 @@ def gen_ngp():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ['unet', 'plms', 'ngp']
+    which = sys.argv[1:] or ['unet', 'plms', 'ngp', 'vae']
     torch.set_num_threads(os.cpu_count())
     if 'unet' in which:
         gen_unet()
@@ -119,3 +138,5 @@ if __name__ == '__main__':
         gen_plms()
     if 'ngp' in which:
         gen_ngp()
+    if 'vae' in which:
+        gen_vae()

@@ -336,7 +336,7 @@ def sample_pdf(bins, weights, n_samples, det=False, u=None):
 
 
 def run(field: Field, rays_o, rays_d, *, num_steps=64, upsample_steps=64, min_near=0.1, bg_color=0.0, perturb_noise=None,
-        pdf_noise=None, training=True, aabb=None):
+        pdf_noise=None, training=True, aabb=None, z_sorted_override=None):
     """renderer_df.py:310-468 for shading='albedo', bg_radius=0.  rays_o/d [N,3] torch fp32.
     perturb_noise [N,num_steps] U(0,1) or None (perturb=False); pdf_noise [N,upsample_steps] U(0,1)
     (ignored when not training: det sampling, :392)."""
@@ -370,6 +370,12 @@ def run(field: Field, rays_o, rays_d, *, num_steps=64, upsample_steps=64, min_ne
         z_vals, z_index = torch.sort(z_vals, dim=1)
         xyzs = torch.cat([xyzs, new_xyzs], dim=1)
         xyzs = torch.gather(xyzs, dim=1, index=z_index.unsqueeze(-1).expand_as(xyzs))
+        if z_sorted_override is not None:
+            # the inverse-CDF resampling is ill-conditioned where the pdf sits on its 1e-5 floor; to compare the stages AFTER it
+            # (field at the samples, compositing, all gradients) tightly, both sides can be fed the same merged depths
+            z_vals = z_sorted_override
+            xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
+            xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
     # The reference evaluates density(new_xyzs) and gathers the coarse+fine sigmas through the sort
     # (:398-412); those sigmas only feed `weights`, and the colour pass (:424) re-evaluates the field
     # at the identical sorted points.  Evaluating once at the sorted points gives the same values

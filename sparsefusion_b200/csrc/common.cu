@@ -1,6 +1,7 @@
 // common.cu -- error reporting and device queries shared by every translation unit
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/sparsefusion_b200.h"
 
 namespace sfb {
@@ -20,7 +21,11 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches += (unsigned long long)n; }
+
 int check_launch(const char* what) {
+    g_launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
     return SFB_OK;
@@ -55,6 +60,7 @@ int sfb_set_precision(int mode) {
     return SFB_OK;
 }
 int sfb_get_precision(void) { return sfb::precision_mode(); }
+uint64_t sfb_launch_count(void) { return (uint64_t)sfb::g_launches.load(); }
 
 int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -18,7 +18,8 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 template <typename T>
 static inline __host__ __device__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
-int check_launch(const char* what);
+int check_launch(const char* what);   // also counts one kernel launch (sfb_launch_count)
+void count_launches(int n);            // extra launches made under a single check_launch
 
 // tensor-core operand precision of the UNet GEMMs: 0 = TF32 single pass, 1 = 3xTF32 (error compensated)
 int precision_mode();

@@ -23,6 +23,7 @@
 #include "../../include/sparsefusion_b200.h"
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 #include <string.h>
 
 namespace sfb {
@@ -303,6 +304,11 @@ static int make_map(CUtensorMap* out, const void* base, const uint64_t dims[4], 
     return SFB_OK;
 }
 
+// optional per-launch timing of the conv kernel (CUDA events on the launch stream) for bench.py's roofline line
+static bool g_prof = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static double g_prof_bytes = 0.0, g_prof_flops = 0.0;
+
 template <int BN, int NP>
 static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
@@ -310,7 +316,17 @@ static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
         SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NP>::kSmemBytes));
         configured = true;
     }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof) {
+        SFB_CUDA(cudaEventCreate(&e0));
+        SFB_CUDA(cudaEventCreate(&e1));
+        SFB_CUDA(cudaEventRecord(e0, st));
+    }
     conv_gemm_tf32_kernel<BN, NP><<<grid, kThreads, ConvCfg<BN, NP>::kSmemBytes, st>>>(p);
+    if (g_prof) {
+        SFB_CUDA(cudaEventRecord(e1, st));
+        g_prof_events.emplace_back(e0, e1);
+    }
     return check_launch("conv2d_nhwc_tf32");
 }
 
@@ -328,6 +344,32 @@ extern "C" {
 
 int sfb_conv_set_tma_tf32(int enable) {
     g_tma_tf32_type = enable ? 1 : 0;
+    return SFB_OK;
+}
+
+int sfb_conv_prof_enable(int on) {
+    g_prof = on != 0;
+    if (on) { g_prof_bytes = 0.0; g_prof_flops = 0.0; }
+    return SFB_OK;
+}
+
+/* sums the recorded conv launches: kernel time (ms), launch count, algorithmic weight bytes and FLOPs (2*MAC); clears the record */
+int sfb_conv_prof_collect(double* total_ms, int* launches, double* weight_bytes, double* flops) {
+    double t = 0.0;
+    for (auto& pr : g_prof_events) {
+        SFB_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        SFB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        t += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (total_ms) *total_ms = t;
+    if (launches) *launches = (int)g_prof_events.size();
+    if (weight_bytes) *weight_bytes = g_prof_bytes;
+    if (flops) *flops = g_prof_flops;
+    g_prof_events.clear();
+    g_prof_bytes = 0.0; g_prof_flops = 0.0;
     return SFB_OK;
 }
 
@@ -420,6 +462,10 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
         SFB_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)Cout * 4, (size_t)NB * Ho * Wo, st));
     }
     dim3 grid(tiles_m, tiles_c, splits);
+    if (g_prof) {
+        g_prof_bytes += (double)Cout * KH * KW * Cin * 4.0;
+        g_prof_flops += 2.0 * NB * Ho * Wo * (double)Cout * KH * KW * Cin;
+    }
     if (precision_mode() == 1) {
         switch (BN) {
             case 32: return launch_conv<32, 3>(p, grid, st);

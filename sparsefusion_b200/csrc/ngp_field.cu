@@ -400,6 +400,7 @@ extern "C" {
 int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* rays_d, const float* z, uint32_t T, uint32_t B,
                           const float* embeddings, const int32_t* offsets, float S, uint32_t H, float bound, const float* W0, const float* b0,
                           const float* W1, const float* b1, const float* W2, const float* b2, float* sigma, float* rgb, void* stream) {
+    if (B == 0) return SFB_OK;
     SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && sigma, "ngp_field_forward: null pointer");
     SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_forward: give xyz or (rays_o, rays_d, z, T)");
     if (B == 0) return SFB_OK;
@@ -419,6 +420,7 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
                            const float* W1, const float* b1, const float* W2, const float* b2, const float* grad_sigma, const float* grad_rgb,
                            float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* tape,
                            void* stream) {
+    if (B == 0) return SFB_OK;
     SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && grad_sigma && grad_embeddings && gW0 && gb0 && gW1 && gb1 && gW2 &&
                     gb2 && tape,
                 "ngp_field_backward: null pointer");
@@ -444,6 +446,7 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
     mlp_wgrad_kernel<kHid, kIn><<<wb, 256, 0, st>>>(D1, H0, Bp, gW0, gb0);
     mlp_wgrad_kernel<kHid, kHid><<<wb, 256, 0, st>>>(D2, H1, Bp, gW1, gb1);
     mlp_wgrad_kernel<kOut, kHid><<<wb, 256, 0, st>>>(D3, H2, Bp, gW2, gb2);
+    count_launches(2);
     return check_launch("ngp_field_backward(weights)");
 }
 

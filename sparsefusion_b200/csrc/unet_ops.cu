@@ -106,15 +106,18 @@ __global__ void pixel_shuffle_silu_kernel(const float* __restrict__ y, float* __
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
-// one CTA per (group, n): mean / rstd over H*W*Cg elements (two-pass-free: fp64 accumulation of sum, sumsq)
-__global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps,
+// CTAs (group, n, pixel-slab): partial fp64 (sum, sumsq) per slab; the last slab to finish folds the partials into (mean, rstd).
+// `counters` is a persistent zero-initialised buffer (one uint per (n, group)); the finishing CTA resets its counter.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps, int S,
+                                                      double2* __restrict__ partial, unsigned int* __restrict__ counters,
                                                       float2* __restrict__ stats) {
-    const int g = blockIdx.x, n = blockIdx.y;
+    const int g = blockIdx.x, n = blockIdx.y, sl = blockIdx.z;
     const int Cg = C / G;
     const int Cg4 = Cg >> 2;
-    const float* base = x + (int64_t)n * HW * ldx + g * Cg;
+    const int p0 = (int)(((int64_t)HW * sl) / S), p1 = (int)(((int64_t)HW * (sl + 1)) / S);
+    const float* base = x + ((int64_t)n * HW + p0) * ldx + g * Cg;
     double s = 0.0, ss = 0.0;
-    const int64_t total4 = (int64_t)HW * Cg4;
+    const int64_t total4 = (int64_t)(p1 - p0) * Cg4;
     for (int64_t i = threadIdx.x; i < total4; i += blockDim.x) {
         const int64_t pix = i / Cg4;
         const int c4 = (int)(i - pix * Cg4);
@@ -124,24 +127,35 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__
         s += (double)a;
         ss += (double)b;
     }
-    __shared__ double sh_s[16], sh_ss[16];
+    __shared__ double sh_s[8], sh_ss[8];
+    __shared__ bool is_last;
     s = warp_sum_d(s);
     ss = warp_sum_d(ss);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
     __syncthreads();
-    if (warp == 0) {
+    if (threadIdx.x == 0) {
         const int nw = blockDim.x >> 5;
-        s = lane < nw ? sh_s[lane] : 0.0;
-        ss = lane < nw ? sh_ss[lane] : 0.0;
-        s = warp_sum_d(s);
-        ss = warp_sum_d(ss);
-        if (lane == 0) {
+        s = 0.0; ss = 0.0;
+        for (int w = 0; w < nw; ++w) { s += sh_s[w]; ss += sh_ss[w]; }
+        const int slot = n * G + g;
+        partial[(int64_t)slot * S + sl] = make_double2(s, ss);
+        __threadfence();
+        const unsigned int done = atomicAdd(&counters[slot], 1u);
+        is_last = (done == (unsigned int)(S - 1));
+        if (is_last) {
+            __threadfence();
+            double ts = 0.0, tss = 0.0;
+            for (int k = 0; k < S; ++k) {
+                const volatile double* pr = reinterpret_cast<volatile double*>(&partial[(int64_t)slot * S + k]);
+                ts += pr[0]; tss += pr[1];
+            }
             const double cnt = (double)HW * Cg;
-            const double mean = s / cnt;
-            double var = ss / cnt - mean * mean;
+            const double mean = ts / cnt;
+            double var = tss / cnt - mean * mean;
             if (var < 0) var = 0;
-            stats[n * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+            stats[slot] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+            counters[slot] = 0u;
         }
     }
 }
@@ -180,31 +194,38 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const 
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm over the last dim
-// rows [T, C] (row stride ldx); y = LN(pre(x)) * g (+ b); pre: 0 none, 1 GELU.  One warp per row.  eps 1e-5, biased variance.
-__global__ void layernorm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, const float* __restrict__ b,
-                                      const float* __restrict__ res, int64_t ldr, float* __restrict__ y, int64_t ldy, int T, int C, int pre,
-                                      int round) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= T) return;
-    const int lane = threadIdx.x & 31;
+// rows [T, C] (row stride ldx); y = LN(pre(x)) * g (+ b) (+ res); pre: 0 none, 1 GELU.  One 128-thread CTA per row.  eps 1e-5, biased variance.
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float t = sh[0] + sh[1] + sh[2] + sh[3];
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(128) layernorm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
+                                                            const float* __restrict__ b, const float* __restrict__ res, int64_t ldr,
+                                                            float* __restrict__ y, int64_t ldy, int T, int C, int pre, int round) {
+    __shared__ float sh[4];
+    const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * ldx;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = threadIdx.x; c < C; c += 128) {
         float v = xr[c];
         if (pre == 1) v = gelu_f(v);
         s += v;
     }
-    const float mean = warp_sum(s) / C;
+    const float mean = block_sum_128(s, sh) / C;
     float ss = 0.f;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = threadIdx.x; c < C; c += 128) {
         float v = xr[c];
         if (pre == 1) v = gelu_f(v);
         const float d = v - mean;
         ss += d * d;
     }
-    const float rstd = rsqrtf(warp_sum(ss) / C + 1e-5f);
+    const float rstd = rsqrtf(block_sum_128(ss, sh) / C + 1e-5f);
     float* yr = y + (int64_t)row * ldy;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = threadIdx.x; c < C; c += 128) {
         float v = xr[c];
         if (pre == 1) v = gelu_f(v);
         float o = (v - mean) * rstd * g[c] + (b ? b[c] : 0.f);
@@ -378,36 +399,49 @@ __global__ void gca_logits_kernel(const float* __restrict__ x, int64_t ldx, cons
     d = warp_sum(d);
     if (lane == 0) logits[p] = d + bk[0];
 }
-// pooled[n][c] = sum_p softmax_p(logits[n])[p] * x[n][p][c]      grid (ceil(C/128), NB), 128 threads = channels, HW <= 4096... any
-__global__ void __launch_bounds__(128) gca_pool_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
-                                                      float* __restrict__ pooled, int HW, int C) {
-    extern __shared__ float wts[];  // [HW]
-    const int n = blockIdx.y;
+// softmax statistics of one image's logits -> stat[n] = (max, 1/sum exp); also zeroes pooled[n][:] for the accumulation pass
+__global__ void __launch_bounds__(256) gca_stats_kernel(const float* __restrict__ logits, float2* __restrict__ stat, float* __restrict__ pooled,
+                                                       int HW, int C) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
     const float* lg = logits + (int64_t)n * HW;
-    __shared__ float red[4];
     float mx = -INFINITY;
-    for (int p = threadIdx.x; p < HW; p += 128) mx = fmaxf(mx, lg[p]);
+    for (int p = threadIdx.x; p < HW; p += 256) mx = fmaxf(mx, lg[p]);
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    mx = red[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
     __syncthreads();
-    float s = 0.f;
-    for (int p = threadIdx.x; p < HW; p += 128) {
-        const float e = __expf(lg[p] - mx);
-        wts[p] = e;
-        s += e;
+    float sm = 0.f;
+    for (int p = threadIdx.x; p < HW; p += 256) sm += __expf(lg[p] - mx);
+    sm = warp_sum(sm);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        stat[n] = make_float2(mx, 1.f / t);
     }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    for (int c = threadIdx.x; c < C; c += 256) pooled[(int64_t)n * C + c] = 0.f;
+}
+// pooled[n][c] += sum_{p in slab} softmax(logits)[p] * x[n][p][c]      grid (slabs of 16 pixels, NB), threads = channels
+__global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
+                                                      const float2* __restrict__ stat, float* __restrict__ pooled, int HW, int C) {
+    constexpr int SLAB = 16;
+    __shared__ float wts[SLAB];
+    const int n = blockIdx.y, p0 = blockIdx.x * SLAB;
+    const int np = min(SLAB, HW - p0);
+    const float2 st = stat[n];
+    if (threadIdx.x < np) wts[threadIdx.x] = __expf(logits[(int64_t)n * HW + p0 + threadIdx.x] - st.x) * st.y;
     __syncthreads();
-    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= C) return;
-    const float* xb = x + (int64_t)n * HW * ldx + c;
-    float acc = 0.f;
-    for (int p = 0; p < HW; ++p) acc += wts[p] * __ldg(xb + (int64_t)p * ldx);
-    pooled[(int64_t)n * C + c] = acc * inv;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float* xb = x + ((int64_t)n * HW + p0) * ldx + c;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int p = 0; p < np; ++p) acc += wts[p] * __ldg(xb + (int64_t)p * ldx);
+        atomicAdd(pooled + (int64_t)n * C + c, acc);
+    }
 }
 
 // out = h * gate[n][c] + res      (ResnetBlock tail, imagen_pytorch.py:727-729); gate may be null (== 1)
@@ -471,12 +505,21 @@ int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W
     return check_launch("pixel_shuffle_silu");
 }
 
+int sfb_groupnorm_ws_floats(int NB, int G) { return ((2 * NB * G + 3) / 4) * 4 + NB * G * 64 * 4; }
+
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
-                       int64_t film_ld, int act_silu, float eps, float* stats_ws, float* y, int64_t ldy, void* stream) {
+                       int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy, void* stream) {
     SFB_REQUIRE(x && gamma && beta && stats_ws && y, "groupnorm_nhwc: null pointer");
+    SFB_REQUIRE(((uintptr_t)stats_ws & 15) == 0, "groupnorm_nhwc: workspace must be 16-byte aligned");
     SFB_REQUIRE(C % G == 0 && (C / G) % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "groupnorm_nhwc: channels per group must be a multiple of 4");
     cudaStream_t st = as_stream(stream);
-    gn_stats_kernel<<<dim3(G, NB), 512, 0, st>>>(x, ldx, HW, C, G, eps, reinterpret_cast<float2*>(stats_ws));
+    // workspace: [0, 2*NB*G) floats = (mean, rstd); then 16-byte aligned fp64 partials [NB*G*S][2]
+    int S = 1;
+    while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
+    float2* stats = reinterpret_cast<float2*>(stats_ws);
+    double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
+    SFB_REQUIRE(counters != nullptr, "groupnorm_nhwc: counters workspace is null");
+    gn_stats_kernel<<<dim3(G, NB, S), 256, 0, st>>>(x, ldx, HW, C, G, eps, S, partial, counters, stats);
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t total4 = (int64_t)NB * HW * (C / 4);
     gn_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
@@ -487,7 +530,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
                        int C, int pre_gelu, int round_tf32, void* stream) {
     SFB_REQUIRE(x && g && y, "layernorm_rows: null pointer");
-    layernorm_rows_kernel<<<ceil_div(T, 8), 256, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
+    layernorm_rows_kernel<<<T, 128, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
     return check_launch("layernorm_rows");
 }
 
@@ -540,14 +583,16 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
 int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
                  void* stream) {
     SFB_REQUIRE(x && wk && bk && logits_ws && pooled, "gca_pool: null pointer");
-    SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && (size_t)HW * 4 <= 160 * 1024, "gca_pool: unsupported shape");
+    SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0, "gca_pool: unsupported shape");
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)NB * HW;
     gca_logits_kernel<<<(unsigned)ceil_div(npix, (int64_t)8), 256, 0, st>>>(x, ldx, wk, bk, logits_ws, npix, C);
     if (int rc = check_launch("gca_pool(logits)")) return rc;
-    static bool cfg = false;
-    if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(gca_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg = true; }
-    gca_pool_kernel<<<dim3(ceil_div(C, 128), NB), 128, (size_t)HW * 4, st>>>(x, ldx, logits_ws, pooled, HW, C);
+    // logits_ws: NB*HW logits followed by NB (max, 1/sum) pairs
+    float2* stat = reinterpret_cast<float2*>(logits_ws + ((npix + 1) / 2) * 2);
+    gca_stats_kernel<<<NB, 256, 0, st>>>(logits_ws, stat, pooled, HW, C);
+    if (int rc = check_launch("gca_pool(stats)")) return rc;
+    gca_pool_kernel<<<dim3(ceil_div(HW, 16), NB), 256, 0, st>>>(x, ldx, logits_ws, stat, pooled, HW, C);
     return check_launch("gca_pool(pool)");
 }
 

