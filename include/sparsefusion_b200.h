@@ -138,6 +138,8 @@ int sfb_conv_weight_k(int Cin, int KH, int KW);
 /* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
 int sfb_conv_prof_enable(int on);
 int sfb_conv_prof_collect(double* total_ms, int* launches, double* weight_bytes, double* flops);
+/* 3xTF32 kernel generation: 2 (default) = M-side operand through tensor memory + swap-AB for <= 64 output pixels; 1 = all-smem split */
+int sfb_conv_set_variant(int v);
 /* experiment switch: encode activation/weight tensor maps as TFLOAT32 instead of FLOAT32 */
 int sfb_conv_set_tma_tf32(int enable);
 

@@ -20,6 +20,7 @@
 // layer's weight stream over all 148 SMs); large-batch layers by the tensor pipe.
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "conv_common.cuh"
 #include "../../include/sparsefusion_b200.h"
 #include <mutex>
 #include <unordered_map>
@@ -27,28 +28,6 @@
 #include <string.h>
 
 namespace sfb {
-
-constexpr int kBM = 128;           // output pixels per CTA (UMMA M)
-constexpr int kBK = 32;            // fp32 elements per k-step: one 128-byte swizzle row
-constexpr int kABytes = kBM * 128; // 16 KB per stage
-constexpr int kThreads = 192;
-
-struct alignas(64) ConvGemmParams {
-    CUtensorMap tmA[4];
-    CUtensorMap tmB;
-    float* out;
-    const float* bias;
-    const float* residual;  // optional [pixel][ldr] tensor added to the result (by split 0)
-    int64_t ldo;            // floats between consecutive output pixels
-    int64_t ldr;
-    int32_t NB, Ho, Wo;
-    int32_t TW, TH, TN;
-    int32_t tiles_w, tiles_h;
-    int32_t Cout, cin_chunks;
-    int32_t KH, KW, pad, stride;
-    int32_t k_iters, splits;
-    int32_t accumulate;
-};
 
 // NP = 1: single-pass TF32 (operands are expected TF32-rounded).  NP = 3: error-compensated "3xTF32": the epilogue
 // warps split every landed stage into hi (= what the tensor core keeps of the raw fp32 word) and lo = x - hi in shared
@@ -254,7 +233,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int g_tma_tf32_type = 0;  // 0: FLOAT32 loads (hardware truncates to tf32); 1: TFLOAT32 tensor-map type
+static int g_tma_tf32_type = 0;
+static int g_variant = 2;         // 3xTF32 kernel generation: 1 = all operands split in smem, 2 = M-side through TMEM (+ swap-AB)  // 0: FLOAT32 loads (hardware truncates to tf32); 1: TFLOAT32 tensor-map type
 
 struct MapKey {
     uint64_t v[12];
@@ -309,6 +289,22 @@ static bool g_prof = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static double g_prof_bytes = 0.0, g_prof_flops = 0.0;
 
+static cudaEvent_t g_prof_e0 = nullptr;
+int conv_prof_begin(cudaStream_t st) {
+    if (!g_prof) return SFB_OK;
+    cudaEvent_t e1 = nullptr;
+    SFB_CUDA(cudaEventCreate(&g_prof_e0));
+    SFB_CUDA(cudaEventCreate(&e1));
+    SFB_CUDA(cudaEventRecord(g_prof_e0, st));
+    g_prof_events.emplace_back(g_prof_e0, e1);
+    return SFB_OK;
+}
+int conv_prof_end(cudaStream_t st) {
+    if (!g_prof) return SFB_OK;
+    SFB_CUDA(cudaEventRecord(g_prof_events.back().second, st));
+    return SFB_OK;
+}
+
 template <int BN, int NP>
 static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
@@ -316,17 +312,9 @@ static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
         SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NP>::kSmemBytes));
         configured = true;
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_prof) {
-        SFB_CUDA(cudaEventCreate(&e0));
-        SFB_CUDA(cudaEventCreate(&e1));
-        SFB_CUDA(cudaEventRecord(e0, st));
-    }
+    conv_prof_begin(st);
     conv_gemm_tf32_kernel<BN, NP><<<grid, kThreads, ConvCfg<BN, NP>::kSmemBytes, st>>>(p);
-    if (g_prof) {
-        SFB_CUDA(cudaEventRecord(e1, st));
-        g_prof_events.emplace_back(e0, e1);
-    }
+    conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32");
 }
 
@@ -373,6 +361,12 @@ int sfb_conv_prof_collect(double* total_ms, int* launches, double* weight_bytes,
     return SFB_OK;
 }
 
+int sfb_conv_set_variant(int v) {
+    if (v != 1 && v != 2) return fail(SFB_ERR_ARG, "conv_set_variant: 1 or 2");
+    g_variant = v;
+    return SFB_OK;
+}
+
 int sfb_conv_weight_k(int Cin, int KH, int KW) { return KH * KW * ((Cin + 31) / 32) * 32; }
 
 int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW, int stride,
@@ -390,13 +384,18 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
 
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
-    // pixel tile: TW x TH x TN = 128 output pixels
+    // pixel tile.  Normal: TW x TH x TN = 128 output pixels on the M side.  Swap-AB (v2, <= 64 output pixels in total): the pixels
+    // are the N side (16 / 32 / 64 of them) and 128 output channels the M side.
     const int planeW = (stride == 2) ? W / 2 : W, planeH = (stride == 2) ? H / 2 : H;
-    p.TW = Wo >= 128 ? 128 : pow2_floor(Wo);
-    if (p.TW < Wo && Wo < 128) p.TW = pow2_floor(Wo);  // non power-of-two widths: several tiles per row
-    p.TH = 128 / p.TW;
+    const int64_t P_total = (int64_t)NB * Ho * Wo;
+    const bool v2 = (precision_mode() == 1 && g_variant == 2);
+    const bool swap = v2 && P_total <= 64 && bn <= 0;
+    int tile_pix = kBM;
+    if (swap) { tile_pix = 16; while (tile_pix < P_total) tile_pix *= 2; }
+    p.TW = Wo >= tile_pix ? tile_pix : pow2_floor(Wo);
+    p.TH = tile_pix / p.TW;
     if (p.TH > Ho) p.TH = pow2_floor(Ho);
-    p.TN = 128 / (p.TW * p.TH);
+    p.TN = tile_pix / (p.TW * p.TH);
     p.tiles_w = ceil_div(Wo, p.TW);
     p.tiles_h = ceil_div(Ho, p.TH);
     const int tiles_n = ceil_div(NB, p.TN);
@@ -417,9 +416,10 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
         BN = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 32));
         const int sms = sm_count();
         while (BN > 128 && tiles_m * ceil_div(Cout, BN) < sms) BN /= 2;  // prefer more CTAs when the grid is small
+        if (v2 && BN > 128) BN = 128;
     }
     SFB_REQUIRE(BN == 32 || BN == 64 || BN == 128 || BN == 256, "conv2d_nhwc_tf32: bn must be 32, 64, 128 or 256");
-    const int tiles_c = ceil_div(Cout, BN);
+    const int tiles_c = swap ? ceil_div(Cout, kBM) : ceil_div(Cout, BN);
     if (splits <= 0) {
         const int ctas = tiles_m * tiles_c;
         splits = 1;
@@ -436,6 +436,7 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
     // tensor maps: activations (1 map, or 4 parity planes for stride 2) and packed weights
     cudaStream_t st = as_stream(stream);
     const uint32_t boxA[4] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    const int w_rows = swap ? kBM : BN;   // rows of the weight box
     if (stride == 1) {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
         const uint64_t strides[3] = {(uint64_t)ldx * 4, (uint64_t)W * ldx * 4, (uint64_t)H * W * ldx * 4};
@@ -453,7 +454,7 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
         const uint64_t ktot = (uint64_t)KH * KW * cin_pad;
         const uint64_t dims[4] = {ktot, (uint64_t)Cout, 1, 1};
         const uint64_t strides[3] = {ktot * 4, 0, 0};
-        const uint32_t boxB[4] = {32u, (uint32_t)BN, 1, 1};
+        const uint32_t boxB[4] = {32u, (uint32_t)w_rows, 1, 1};
         if (int rc = make_map(&p.tmB, w_packed, dims, strides, boxB, 2)) return rc;
     }
 
@@ -466,6 +467,7 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
         g_prof_bytes += (double)Cout * KH * KW * Cin * 4.0;
         g_prof_flops += 2.0 * NB * Ho * Wo * (double)Cout * KH * KW * Cin;
     }
+    if (v2 && (swap || BN <= 128)) return launch_conv_v2(p, swap ? tile_pix : BN, swap, grid, st);
     if (precision_mode() == 1) {
         switch (BN) {
             case 32: return launch_conv<32, 3>(p, grid, st);

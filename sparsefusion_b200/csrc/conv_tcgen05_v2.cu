@@ -1,0 +1,309 @@
+// conv_tcgen05_v2.cu -- second-generation 3xTF32 implicit-GEMM convolution: the M-side operand goes through TENSOR MEMORY.
+//
+// Why: ncu on round-1's kernel (profiles/) shows the error-compensated path is bound by SHARED-MEMORY bandwidth, not HBM: every
+// stage was read by the splitter, written back twice (hi, lo) and then read six more times by the three MMAs per k-step
+// (~190 KB of smem traffic per 32 KB of operands).  Here:
+//   * the 128-row ("M-side") operand tile lands in smem by TMA once, is read ONCE by the converter warps (thread r owns row r,
+//     swizzle-aware LDS.128), split into hi = tf32(x) and lo = x - hi in registers and written to TMEM with tcgen05.st; the MMAs
+//     then take A from TMEM (tcgen05.mma ... [d], [a], b_desc) -- no further smem reads for that operand;
+//   * only the narrow ("N-side") tile stays in smem (hi in place + lo copy);
+//   * SWAP mode for layers with <= 64 output pixels per launch (the 4x4 / 8x8 stages at batch 1, which hold 1.39 of the UNet's
+//     1.60 GB of weights): the WEIGHTS are the M-side operand (128 output channels per CTA, streamed HBM -> smem -> TMEM) and
+//     the pixels the N-side (N = 16/32/64), so the tensor core does no work on padding rows and a stage is 20-32 KB of smem:
+//     6-7 stages = ~100 KB of weights in flight per SM, enough to cover HBM latency at full bandwidth.
+// D = sum over (tap, channel chunk) of  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (fp32 accumulation in TMEM), as in v1.
+// Tiling, tap -> TMA coordinate mapping, split-K, bias / residual / accumulate epilogue semantics are v1's (conv_tcgen05.cu).
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "conv_common.cuh"
+#include "../../include/sparsefusion_b200.h"
+#include <string.h>
+
+namespace sfb {
+
+template <int BN>
+struct Conv2Cfg {
+    static constexpr int kNBytes = BN * 128;                 // N-side tile (raw == hi after the split)
+    static constexpr int kStageBytes = kABytes + 2 * kNBytes;  // M raw | N hi | N lo
+    static constexpr int kDCols = BN < 32 ? 32 : BN;          // accumulator columns
+    static constexpr int kABase = kDCols < 64 ? 64 : kDCols;  // first TMEM column of the A-operand ring
+    static constexpr int kStagesSmem = (200 * 1024) / kStageBytes;
+    static constexpr int kStagesTmem = (512 - kABase) / 64;   // 32 hi + 32 lo columns per stage
+    static constexpr int kStages = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024 + 512;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A from tensor memory, B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// SWAP == false: M-side = 128 output pixels (tmA), N-side = BN output channels (tmB).
+// SWAP == true : M-side = 128 output channels (tmB), N-side = BN output pixels (tmA, box {32, TW, TH, TN} with TW*TH*TN == BN).
+template <int BN, bool SWAP>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = Conv2Cfg<BN>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + S;
+    uint64_t* conv_bar = empty_bar + S;
+    uint64_t* tmem_full_bar = conv_bar + S;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 512);   // up to 256 floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tw_i = tile % p.tiles_w, th_i = (tile / p.tiles_w) % p.tiles_h, tn_i = tile / (p.tiles_w * p.tiles_h);
+    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+    const int cout0 = blockIdx.y * (SWAP ? kBM : BN);
+    const int kb = (int)(((int64_t)p.k_iters * blockIdx.z) / p.splits);
+    const int ke = (int)(((int64_t)p.k_iters * (blockIdx.z + 1)) / p.splits);
+    const int niter = ke - kb;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); tc::mbar_init(&conv_bar[i], 4); }
+        tc::mbar_init(tmem_full_bar, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tensormap(&p.tmA[0]);
+        tc::prefetch_tensormap(&p.tmB);
+    }
+    if (warp == 1) tc::tmem_alloc<512>(tmem_holder);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (tc::elect_one()) {
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                tc::mbar_expect_tx(&full_bar[s], kABytes + Cfg::kNBytes);
+                const int i = kb + it;
+                const int tap = i / p.cin_chunks, cc = i - tap * p.cin_chunks;
+                const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                int oy = ky - p.pad, ox = kx - p.pad, map = 0;
+                if (p.stride == 2) {
+                    const int py = oy & 1, px = ox & 1;
+                    map = py * 2 + px;
+                    oy = (oy - py) >> 1;
+                    ox = (ox - px) >> 1;
+                }
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                uint8_t* act_dst = SWAP ? st + kABytes : st;
+                uint8_t* wgt_dst = SWAP ? st : st + kABytes;
+                tc::tma_load_4d(act_dst, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
+                tc::tma_load_2d(wgt_dst, &p.tmB, &full_bar[s], i * kBK, cout0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(kBM, BN);
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                tc::mbar_wait(&conv_bar[s], ph);
+                tc::fence_after_sync();
+                const uint32_t b_hi = tc::smem_u32(smem + s * Cfg::kStageBytes + kABytes), b_lo = b_hi + Cfg::kNBytes;
+                const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::kABase + 64 * s), a_lo = a_hi + 32;
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {
+                    const uint64_t dbh = tc::umma_desc_k_sw128(b_hi + k * 32), dbl = tc::umma_desc_k_sw128(b_lo + k * 32);
+                    umma_tf32_ts(tmem_base, a_hi + k * 8, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32_ts(tmem_base, a_lo + k * 8, dbh, idesc, 1u);
+                    umma_tf32_ts(tmem_base, a_hi + k * 8, dbl, idesc, 1u);
+                }
+                tc::umma_commit(&empty_bar[s]);
+            }
+            tc::umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ------------------------------------------------------------ converter + epilogue (warps 2..5)
+        const int et = threadIdx.x - 64;   // 0..127
+        const int q = warp & 3;            // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;       // M-side row owned by this thread
+        const int nb = SWAP ? kBM : BN;
+        for (int i = et; i < nb; i += 128) {
+            const int c = cout0 + i;
+            bias_s[i] = (p.bias != nullptr && blockIdx.z == 0 && c < p.Cout) ? p.bias[c] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int it = 0; it < niter; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            tc::mbar_wait(&full_bar[s], ph);
+            uint8_t* st = smem + s * Cfg::kStageBytes;
+            // (1) M-side row r: 8 swizzled 16-byte chunks -> hi / lo -> TMEM columns [kABase + 64 s, +32) / [+32, +64)
+            {
+                const uint8_t* rowp = st + r * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+                    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+                        hi[c * 4 + e] = h;
+                        lo[c * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
+                    }
+                }
+                const uint32_t ta = lane_addr + (uint32_t)(Cfg::kABase + 64 * s);
+                tmem_st_32x32(ta, hi);
+                tmem_st_32x32(ta + 32, lo);
+            }
+            // (2) N-side tile: hi in place, lo to the second buffer (same offsets => same swizzled layout)
+            {
+                float4* nraw = reinterpret_cast<float4*>(st + kABytes);
+                float4* nlo = reinterpret_cast<float4*>(st + kABytes + Cfg::kNBytes);
+#pragma unroll 2
+                for (int i = et; i < BN * 8; i += 128) {
+                    const float4 v = nraw[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    nraw[i] = h;
+                    nlo[i] = l;
+                }
+            }
+            tmem_st_wait();
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&conv_bar[s]);
+        }
+
+        // ---- epilogue
+        const bool use_red = (p.splits > 1) || (p.accumulate != 0);
+        tc::mbar_wait(tmem_full_bar, 0);
+        tc::fence_after_sync();
+        if (!SWAP) {
+            const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+            const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+            const bool valid = (n < p.NB) && (h < p.Ho) && (w < p.Wo);
+            const int64_t pix = (int64_t)((int64_t)n * p.Ho + h) * p.Wo + w;
+            float* orow = p.out + pix * p.ldo + cout0;
+            const float* rrow = (p.residual != nullptr && blockIdx.z == 0) ? p.residual + pix * p.ldr + cout0 : nullptr;
+#pragma unroll 1
+            for (int j = 0; j < Cfg::kDCols / 32; ++j) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(lane_addr + (uint32_t)(j * 32), v);
+                tc::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int c = j * 32 + g * 4;
+                        if (c < BN && cout0 + c < p.Cout) {
+                            float x0 = __uint_as_float(v[g * 4 + 0]) + bias_s[c + 0];
+                            float x1 = __uint_as_float(v[g * 4 + 1]) + bias_s[c + 1];
+                            float x2 = __uint_as_float(v[g * 4 + 2]) + bias_s[c + 2];
+                            float x3 = __uint_as_float(v[g * 4 + 3]) + bias_s[c + 3];
+                            if (rrow) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + c));
+                                x0 += rv.x; x1 += rv.y; x2 += rv.z; x3 += rv.w;
+                            }
+                            if (use_red) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c), "f"(x0), "f"(x1), "f"(x2), "f"(x3)
+                                             : "memory");
+                            } else {
+                                *reinterpret_cast<float4*>(orow + c) = make_float4(x0, x1, x2, x3);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            // rows = output channels (this thread: cout0 + r), columns = the BN pixels of the tile
+            const int c = cout0 + r;
+            const bool cvalid = c < p.Cout;
+            const float bv = bias_s[r];
+            const bool add_res = (p.residual != nullptr && blockIdx.z == 0);
+#pragma unroll 1
+            for (int j = 0; j < Cfg::kDCols / 32; ++j) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(lane_addr + (uint32_t)(j * 32), v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int pj = j * 32 + e;                          // pixel index inside the tile (uniform across the warp)
+                    if (pj < BN) {
+                        const int tw = pj % p.TW, th = (pj / p.TW) % p.TH, tn = pj / (p.TW * p.TH);
+                        const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+                        if (cvalid && n < p.NB && h < p.Ho && w < p.Wo) {
+                            const int64_t pix = (int64_t)((int64_t)n * p.Ho + h) * p.Wo + w;
+                            float x = __uint_as_float(v[e]) + bv;
+                            if (add_res) x += __ldg(p.residual + pix * p.ldr + c);
+                            float* dst = p.out + pix * p.ldo + c;
+                            if (use_red) atomicAdd(dst, x);
+                            else *dst = x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int BN, bool SWAP>
+static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_v2_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<BN>::kSmemBytes));
+        configured = true;
+    }
+    conv_prof_begin(st);
+    conv_gemm_v2_kernel<BN, SWAP><<<grid, kThreads, Conv2Cfg<BN>::kSmemBytes, st>>>(p);
+    conv_prof_end(st);
+    return check_launch("conv2d_nhwc_tf32(v2)");
+}
+
+int launch_conv_v2(const ConvGemmParams& p, int BN, bool swap, dim3 grid, cudaStream_t st) {
+    if (swap) {
+        switch (BN) {
+            case 16: return launch_v2<16, true>(p, grid, st);
+            case 32: return launch_v2<32, true>(p, grid, st);
+            default: return launch_v2<64, true>(p, grid, st);
+        }
+    }
+    switch (BN) {
+        case 32: return launch_v2<32, false>(p, grid, st);
+        case 64: return launch_v2<64, false>(p, grid, st);
+        default: return launch_v2<128, false>(p, grid, st);
+    }
+}
+
+}  // namespace sfb

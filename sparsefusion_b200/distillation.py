@@ -68,7 +68,7 @@ class FlatAdam:
     the update a single fused kernel per parameter group (encoder lr*10, MLP lr: network_grid.py:223-234)."""
 
     def __init__(self, net, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, step_size=3000, gamma=0.2):
-        groups = net.get_params(lr)
+        groups = [dict(g, params=list(g['params'])) for g in net.get_params(lr)]   # get_params hands out generators
         params = [p for g in groups for p in g['params']]
         dev = params[0].device
         sizes = [p.numel() for p in params]

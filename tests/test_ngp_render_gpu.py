@@ -122,7 +122,8 @@ def test_run_render_vs_oracle_and_golden(golden_dir):
     # eval mode: deterministic importance sampling (det=True), no perturbation, render_batched chunks
     net.eval()
     with torch.no_grad():
-        e = net.render_batched(dev(ro)[None], dev(rd)[None], batched=True, max_ray_batch=500, bg_color=0, perturb=False, shading='albedo', **vars(opt))
+        kw = dict(vars(opt), max_ray_batch=500)
+        e = net.render_batched(dev(ro)[None], dev(rd)[None], batched=True, bg_color=0, perturb=False, shading='albedo', **kw)
     ref = no.run(no.Field(p, level_scales=_device_scales(no.live_geometry())), torch.from_numpy(ro), torch.from_numpy(rd), training=False)
     assert _rel(e['image'][0], ref['image']) < 1e-3
 
