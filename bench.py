@@ -218,7 +218,9 @@ def run_gpu(args):
         _lib.call('sfb_conv_prof_enable', 1)
         reps = 5
         for _ in range(reps):
-            unet.forward(x, t, cond_images=c)
+            torch.cuda._sleep(int(2e7))   # ~10 ms of GPU idle-spin: the CPU enqueues the whole eager evaluation behind it, so the
+            unet.forward(x, t, cond_images=c)   # events around each conv launch measure kernel time, not CPU launch gaps
+            torch.cuda.synchronize()
         import ctypes
         tot, nl, wb, fl = ctypes.c_double(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
         _lib.load().sfb_conv_prof_collect(ctypes.byref(tot), ctypes.byref(nl), ctypes.byref(wb), ctypes.byref(fl))

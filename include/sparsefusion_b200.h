@@ -42,6 +42,9 @@ int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * to TF32 where they are produced; ~1.5e-3 relative error on the UNet output, ~1/3 of the tensor-pipe work. */
 int sfb_set_precision(int mode);
 int sfb_get_precision(void);
+/* experiment switch (default on): every kernel requests the maximum shared-memory carve-out so that consecutive launches never make the SMs
+ * re-partition L1 / shared memory.  Only affects kernels launched for the first time after the call. */
+int sfb_set_carveout(int on);
 /* number of kernels this library has launched so far in this process (bench.py's "gpu_launches") */
 uint64_t sfb_launch_count(void);
 
@@ -180,6 +183,13 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
 /* ResnetBlock tail (:727-729): out = h * gate[n][c] + res (gate NULL == 1) */
 int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const float* res, int64_t ldr, float* out, int64_t ldo, int NB,
                            int HW, int C, void* stream);
+
+/* PLMSSampler.p_sample tail (external/plms.py:143-154, :183-212) as one elementwise pass over the latent:
+ *   e' = c0*e0 + c1*e1 + c2*e2 + c3*e3 (e1..e3 may be NULL);  x0 = clamp((x - sigma*e') / max(alpha,1e-8), +-clip);
+ *   x_prev = alpha_next * (x*(1-c)/alpha + c*x0) + noise_scale * noise.   x0_out / e_out may be NULL. */
+int sfb_plms_update(const float* x, const float* e0, const float* e1, const float* e2, const float* e3, float c0, float c1, float c2,
+                    float c3, const float* noise, float alpha, float sigma, float alpha_next, float c, float noise_scale, float clip,
+                    float* x_prev, float* x0_out, float* e_out, int64_t n, void* stream);
 
 /* ============================================================================================
  * 4. Fused Instant-NGP field and optimiser   (external/nerf/network_grid.py NeRFNetwork, torch.optim.Adam)

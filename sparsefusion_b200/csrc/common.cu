@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <unordered_set>
 #include "../../include/sparsefusion_b200.h"
 
 namespace sfb {
@@ -35,6 +37,15 @@ static int g_precision = 1;  // 0: single-pass TF32 (operands rounded on write);
 int precision_mode() { return g_precision; }
 void set_precision_mode(int m) { g_precision = m; }
 
+int g_carveout = 1;
+void prefer_smem(const void* kernel) {
+    static std::unordered_set<const void*> done;
+    static std::mutex mu;
+    if (!g_carveout) return;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -60,6 +71,7 @@ int sfb_set_precision(int mode) {
     return SFB_OK;
 }
 int sfb_get_precision(void) { return sfb::precision_mode(); }
+int sfb_set_carveout(int on) { sfb::g_carveout = on != 0; return SFB_OK; }
 uint64_t sfb_launch_count(void) { return (uint64_t)sfb::g_launches.load(); }
 
 int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -25,6 +25,18 @@ void count_launches(int n);            // extra launches made under a single che
 int precision_mode();
 void set_precision_mode(int m);
 
+// Every kernel of the library asks for the maximum shared-memory carve-out, whether it needs it or not: the tcgen05 GEMMs use ~200 KB of
+// smem, and alternating them with small-smem kernels would otherwise make the SMs re-partition L1/smem between consecutive launches.
+void prefer_smem(const void* kernel);
+template <typename... A>
+static inline auto kernel_with_carveout(void (*k)(A...)) -> void (*)(A...) {
+    prefer_smem((const void*)k);
+    return k;
+}
+}  // namespace sfb
+#define SFB_K(...) sfb::kernel_with_carveout(__VA_ARGS__)
+namespace sfb {
+
 // number of SMs of the current device (cached)
 int sm_count();
 

@@ -286,7 +286,9 @@ static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
         configured = true;
     }
     conv_prof_begin(st);
-    conv_gemm_v2_kernel<BN, SWAP><<<grid, kThreads, Conv2Cfg<BN>::kSmemBytes, st>>>(p);
+    void (*kp)(const ConvGemmParams) = conv_gemm_v2_kernel<BN, SWAP>;
+    prefer_smem((const void*)kp);
+    kp<<<grid, kThreads, Conv2Cfg<BN>::kSmemBytes, st>>>(p);
     conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32(v2)");
 }

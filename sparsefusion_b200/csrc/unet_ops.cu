@@ -476,14 +476,14 @@ extern "C" {
 int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream) {
     SFB_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
+    SFB_K(nchw_to_nhwc_kernel)<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
     return check_launch("nchw_to_nhwc");
 }
 
 int sfb_nhwc_to_nchw(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, void* stream) {
     SFB_REQUIRE(src && dst, "nhwc_to_nchw: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    nhwc_to_nchw_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld);
+    SFB_K(nhwc_to_nchw_kernel)<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld);
     return check_launch("nhwc_to_nchw");
 }
 
@@ -492,7 +492,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
     SFB_REQUIRE(a && b && out, "concat2_nhwc: null pointer");
     SFB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0, "concat2_nhwc: channel counts must be multiples of 4");
     const int64_t total = npix * ((C1 + C2) / 4);
-    concat2_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
+    SFB_K(concat2_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
                                                                     reinterpret_cast<const float4*>(b), C2 / 4, ldb / 4, scale_b,
                                                                     reinterpret_cast<float4*>(out), ldo / 4, npix);
     return check_launch("concat2_nhwc");
@@ -501,7 +501,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream) {
     SFB_REQUIRE(y && out, "pixel_shuffle_silu: null pointer");
     const int64_t total = (int64_t)NB * 4 * H * W * Co;
-    pixel_shuffle_silu_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(y, out, H, W, Co, ldo, total);
+    SFB_K(pixel_shuffle_silu_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(y, out, H, W, Co, ldo, total);
     return check_launch("pixel_shuffle_silu");
 }
 
@@ -519,10 +519,10 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     float2* stats = reinterpret_cast<float2*>(stats_ws);
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
     SFB_REQUIRE(counters != nullptr, "groupnorm_nhwc: counters workspace is null");
-    gn_stats_kernel<<<dim3(G, NB, S), 256, 0, st>>>(x, ldx, HW, C, G, eps, S, partial, counters, stats);
+    SFB_K(gn_stats_kernel)<<<dim3(G, NB, S), 256, 0, st>>>(x, ldx, HW, C, G, eps, S, partial, counters, stats);
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t total4 = (int64_t)NB * HW * (C / 4);
-    gn_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
+    SFB_K(gn_apply_kernel)<<<ew_blocks(total4), 256, 0, st>>>(x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
                                                       act_silu, precision_mode() == 0, total4);
     return check_launch("groupnorm_nhwc(apply)");
 }
@@ -530,7 +530,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
                        int C, int pre_gelu, int round_tf32, void* stream) {
     SFB_REQUIRE(x && g && y, "layernorm_rows: null pointer");
-    layernorm_rows_kernel<<<T, 128, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
+    SFB_K(layernorm_rows_kernel)<<<T, 128, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
     return check_launch("layernorm_rows");
 }
 
@@ -543,13 +543,13 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
         const size_t sm = (size_t)2 * K * 4;
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)); cfg = true; }
-        linear_small_kernel<2><<<dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        SFB_K(linear_small_kernel<2>)<<<dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     } else {
         const size_t sm = (size_t)8 * K * 4;
         SFB_REQUIRE(sm <= 200 * 1024, "linear_small: K too large for 8-row tile");
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-        linear_small_kernel<8><<<dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        SFB_K(linear_small_kernel<8>)<<<dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     }
     return check_launch("linear_small");
 }
@@ -557,7 +557,7 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
 int sfb_time_fourier(const float* t, const float* w, float* out, int B, int half, void* stream) {
     SFB_REQUIRE(t && w && out, "time_fourier: null pointer");
     const int total = B * (2 * half + 1);
-    time_fourier_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(t, w, out, B, half);
+    SFB_K(time_fourier_kernel)<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(t, w, out, B, half);
     return check_launch("time_fourier");
 }
 
@@ -568,7 +568,7 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
     const int warps = 4;
     const size_t sm = (size_t)warps * nk * 4;
     SFB_REQUIRE(sm <= 48 * 1024, "mq_attention: too many keys for the single-pass kernel");
-    mq_attention_kernel<<<ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream)>>>(q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    SFB_K(mq_attention_kernel)<<<ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream)>>>(q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("mq_attention");
 }
 
@@ -576,7 +576,7 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
                         void* stream) {
     SFB_REQUIRE(q && kvc && null_kv && out, "cross_attention: null pointer");
     SFB_REQUIRE(nc <= 8, "cross_attention: at most 8 context tokens");
-    cross_attention_kernel<<<ceil_div(B * heads * n, 4), 128, 0, as_stream(stream)>>>(q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    SFB_K(cross_attention_kernel)<<<ceil_div(B * heads * n, 4), 128, 0, as_stream(stream)>>>(q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("cross_attention");
 }
 
@@ -586,13 +586,13 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0, "gca_pool: unsupported shape");
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)NB * HW;
-    gca_logits_kernel<<<(unsigned)ceil_div(npix, (int64_t)8), 256, 0, st>>>(x, ldx, wk, bk, logits_ws, npix, C);
+    SFB_K(gca_logits_kernel)<<<(unsigned)ceil_div(npix, (int64_t)8), 256, 0, st>>>(x, ldx, wk, bk, logits_ws, npix, C);
     if (int rc = check_launch("gca_pool(logits)")) return rc;
     // logits_ws: NB*HW logits followed by NB (max, 1/sum) pairs
     float2* stat = reinterpret_cast<float2*>(logits_ws + ((npix + 1) / 2) * 2);
-    gca_stats_kernel<<<NB, 256, 0, st>>>(logits_ws, stat, pooled, HW, C);
+    SFB_K(gca_stats_kernel)<<<NB, 256, 0, st>>>(logits_ws, stat, pooled, HW, C);
     if (int rc = check_launch("gca_pool(stats)")) return rc;
-    gca_pool_kernel<<<dim3(ceil_div(HW, 16), NB), 256, 0, st>>>(x, ldx, logits_ws, stat, pooled, HW, C);
+    SFB_K(gca_pool_kernel)<<<dim3(ceil_div(HW, 16), NB), 256, 0, st>>>(x, ldx, logits_ws, stat, pooled, HW, C);
     return check_launch("gca_pool(pool)");
 }
 
@@ -601,9 +601,48 @@ int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const
     SFB_REQUIRE(h && res && out, "gate_residual: null pointer");
     SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0, "gate_residual: channel counts must be multiples of 4");
     const int64_t total = (int64_t)NB * HW * (C / 4);
-    gate_residual_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(h), ldh / 4, gate,
+    SFB_K(gate_residual_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(h), ldh / 4, gate,
                                                                           reinterpret_cast<const float4*>(res), ldr / 4,
                                                                           reinterpret_cast<float4*>(out), ldo / 4, HW, C / 4, total);
     return check_launch("gate_residual");
 }
+}
+
+// ------------------------------------------------------------------------------------ PLMS sampler update
+// One fused pass for PLMSSampler.p_sample's tail (external/plms.py:143-154 + get_model_output :183-212):
+//   e' = sum_i coef[i] * eps[i]                                   (Adams-Bashforth combination, :143-152)
+//   x0 = clamp((x - sigma * e') / max(alpha, 1e-8), -clip, clip)  (predict_start_from_noise + clamp, :184,:205)
+//   x_prev = alpha_next * (x * (1 - c) / alpha + c * x0) + noise_scale * noise     (q_posterior mean + sigma_t * z, :208-212)
+// The per-step scalars (alpha, sigma, alpha_next, c, noise_scale = mask * exp(0.5 * log var)) are computed on the host from t, t_next.
+namespace sfb {
+__global__ void plms_update_kernel(const float* __restrict__ x, const float* __restrict__ e0, const float* __restrict__ e1,
+                                   const float* __restrict__ e2, const float* __restrict__ e3, float c0, float c1, float c2, float c3,
+                                   const float* __restrict__ noise, float alpha, float sigma, float alpha_next, float c, float noise_scale,
+                                   float clip, float* __restrict__ x_prev, float* __restrict__ x0_out, float* __restrict__ e_out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float e = c0 * e0[i];
+        if (e1) e += c1 * e1[i];
+        if (e2) e += c2 * e2[i];
+        if (e3) e += c3 * e3[i];
+        const float xv = x[i];
+        float x0 = (xv - sigma * e) / fmaxf(alpha, 1e-8f);
+        x0 = fminf(fmaxf(x0, -clip), clip);
+        const float mean = alpha_next * (xv * (1.f - c) / alpha + c * x0);
+        x_prev[i] = mean + noise_scale * noise[i];
+        if (x0_out) x0_out[i] = x0;
+        if (e_out) e_out[i] = e;
+    }
+}
+}  // namespace sfb
+
+extern "C" int sfb_plms_update(const float* x, const float* e0, const float* e1, const float* e2, const float* e3, float c0, float c1, float c2,
+                               float c3, const float* noise, float alpha, float sigma, float alpha_next, float c, float noise_scale, float clip,
+                               float* x_prev, float* x0_out, float* e_out, int64_t n, void* stream) {
+    if (n == 0) return SFB_OK;
+    SFB_REQUIRE(x && e0 && noise && x_prev, "plms_update: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    SFB_K(sfb::plms_update_kernel)<<<(unsigned)blocks, 256, 0, sfb::as_stream(stream)>>>(x, e0, e1, e2, e3, c0, c1, c2, c3, noise, alpha, sigma, alpha_next, c,
+                                                                                 noise_scale, clip, x_prev, x0_out, e_out, n);
+    return sfb::check_launch("plms_update");
 }

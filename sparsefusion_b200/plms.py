@@ -6,16 +6,42 @@ return values ``(pred_x0, x_noisy, noise, alpha_cumprod)``.  ``n_steps = min(int
 steps, ``n_steps + 1`` UNet evaluations (plms.py:87,136-142), Adams-Bashforth 2/3/4 on the eps history (:144-152),
 clamp of x0 to +-clip_value (:205), stochastic posterior step (:208-212).
 
-B200 notes: each eps evaluation replays one CUDA graph of the UNet (``UnetGraph``); the few-hundred-byte schedule
-math between evaluations stays in torch.  Every ``torch.randn_like`` of the reference is routed through
-``self.noise_fn`` (default ``torch.randn_like``) in the reference's draw order, so parity tests can inject the
-oracle's noise.
+B200 notes: each eps evaluation replays one CUDA graph of the UNet (``UnetGraph``); the schedule scalars (alpha, sigma, c,
+posterior variance) are computed on the host from t / t_next and the whole latent update of a step -- Adams-Bashforth
+combination, x0 prediction + clamp, posterior mean, noise injection: ~30 eager launches in the reference -- is ONE fused
+kernel (``sfb_plms_update``).  Every ``torch.randn_like`` of the reference is routed through ``self.noise_fn`` (default
+``torch.randn_like``) in the reference's draw order and count (including the draws whose result the reference discards), so
+parity tests can inject the oracle's noise.  ``p_sample`` / ``get_model_output`` remain as the
+reference-shaped (unfused) methods; ``plms_sample_loop`` uses the fused path on CUDA.
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
+from . import _lib as lib
 from .imagen_pytorch import GaussianDiffusionContinuousTimes, UnetGraph
+
+
+def _log_snr(t: float, s: float = 0.008) -> float:
+    """alpha_cosine_log_snr (external/imagen_pytorch.py:194-196) for a host scalar"""
+    return -math.log(max(math.cos((t + s) / (1 + s) * math.pi * 0.5) ** -2 - 1, 1e-5))
+
+
+def _sigmoid(x: float) -> float:
+    return 1.0 / (1.0 + math.exp(-x))
+
+
+def _step_scalars(t: float, t_next: float):
+    """alpha, sigma of t and the q_posterior coefficients towards t_next (imagen_pytorch.py:240-258, :293-297)"""
+    ls, lsn = _log_snr(t), _log_snr(t_next)
+    alpha, sigma = math.sqrt(_sigmoid(ls)), math.sqrt(_sigmoid(-ls))
+    alpha_next, sigma_next = math.sqrt(_sigmoid(lsn)), math.sqrt(_sigmoid(-lsn))
+    c = -math.expm1(ls - lsn)
+    var = sigma_next ** 2 * c
+    noise_scale = 0.0 if t_next == 0 else math.exp(0.5 * math.log(max(var, 1e-20)))
+    return alpha, sigma, alpha_next, c, noise_scale
 
 
 class PLMSSampler:
@@ -58,6 +84,8 @@ class PLMSSampler:
             image = torch.randn(shape, device=device)
         else:
             assert max_thres is not None
+        if image.is_cuda and pred_objective == 'noise' and not dynamic_threshold and self.diffusion.clip_output:
+            return self._fused_loop(unet, image.float().contiguous(), cond_images, cond_scale, float(max_thres))
         short = GaussianDiffusionContinuousTimes(noise_schedule='cosine', timesteps=self.plms_steps)
         if max_thres >= .99:
             timesteps = short.get_sampling_timesteps(batch, device=device)
@@ -81,6 +109,64 @@ class PLMSSampler:
         if self.diffusion.clip_output:
             img = img.clamp(-self.diffusion.clip_value, self.diffusion.clip_value)
         return self.diffusion.unnormalize_img(img), x_noisy, noise, torch.sigmoid(log_snr)
+
+    @torch.no_grad()
+    def _fused_loop(self, unet, image, cond_images, cond_scale, max_thres):
+        """plms_sample_loop (:54-119) + p_sample (:122-156) with the per-step latent math in one kernel"""
+        b = image.shape[0]
+        clip = float(self.diffusion.clip_value)
+        if max_thres >= .99:                                                      # :80-85
+            lin = torch.linspace(1., 0., self.plms_steps + 1).tolist()
+            noise = self.noise_fn(image)
+            a0, s0 = math.sqrt(_sigmoid(_log_snr(max_thres))), math.sqrt(_sigmoid(-_log_snr(max_thres)))
+            x_noisy = a0 * image + s0 * noise
+            img = image
+        else:                                                                     # :86-93
+            n_steps = min(int(max_thres * self.plms_steps * 2), self.plms_steps)
+            lin = torch.linspace(max_thres, 0.0, n_steps + 1).tolist()
+            noise = self.noise_fn(image)
+            a0, s0 = math.sqrt(_sigmoid(_log_snr(max_thres))), math.sqrt(_sigmoid(-_log_snr(max_thres)))
+            img = a0 * image + s0 * noise
+            x_noisy = img
+        n = img.numel()
+        st = lib.stream
+
+        def eps_at(x, t):
+            ls = torch.full((b,), _log_snr(t), dtype=torch.float32, device=x.device)
+            return self._eps(unet, x, ls, cond_images, cond_scale)
+
+        def update(x, eps_list, coefs, z, t, t_next):
+            alpha, sigma, alpha_next, c, noise_scale = _step_scalars(t, t_next)
+            out = torch.empty_like(x)
+            ptrs = [lib.fptr(e.contiguous()) for e in eps_list] + [None] * (4 - len(eps_list))
+            cf = list(coefs) + [0.0] * (4 - len(coefs))
+            lib.call('sfb_plms_update', lib.fptr(x), *ptrs, *cf, lib.fptr(z.contiguous()), alpha, sigma, alpha_next, c, noise_scale, clip, lib.fptr(out),
+                     None, None, n, st())
+            return out
+
+        old_eps = []
+        for i in range(len(lin) - 1):
+            t, t_next = lin[i], lin[i + 1]
+            e_t = eps_at(img, t)
+            self.noise_fn(img)                                                    # draw of the first get_model_output call (:136; result unused)
+            if len(old_eps) == 0:                                                 # pseudo improved Euler (:137-143)
+                x_prev = update(img, [e_t], [1.0], self.noise_fn(img), t, t_next)
+                e_next = eps_at(x_prev, t_next)
+                self.noise_fn(x_prev)                                             # draw of the third call (:142; result unused)
+                eps_list, coefs = [e_t, e_next], [0.5, 0.5]
+            elif len(old_eps) == 1:
+                eps_list, coefs = [e_t, old_eps[-1]], [1.5, -0.5]
+            elif len(old_eps) == 2:
+                eps_list, coefs = [e_t, old_eps[-1], old_eps[-2]], [23 / 12, -16 / 12, 5 / 12]
+            else:
+                eps_list, coefs = [e_t, old_eps[-1], old_eps[-2], old_eps[-3]], [55 / 24, -59 / 24, 37 / 24, -9 / 24]
+            img = update(img, eps_list, coefs, self.noise_fn(img), t, t_next)
+            old_eps.append(e_t)
+            if len(old_eps) >= 4:
+                old_eps.pop(0)
+        img = img.clamp(-clip, clip)
+        acp = torch.full((b,), _sigmoid(_log_snr(max_thres)), dtype=torch.float32, device=img.device)
+        return self.diffusion.unnormalize_img(img), x_noisy, noise, acp
 
     @torch.no_grad()
     def p_sample(self, unet, x, t, t_next, cond_images, cond_scale, noise_scheduler, pred_objective, dynamic_threshold, old_eps):

@@ -45,6 +45,9 @@ def conv_cases():
 
 def unet_bench(out):
     import numpy as np
+    if 'nocarve' in sys.argv:
+        from sparsefusion_b200 import _lib
+        _lib.call('sfb_set_carveout', 0)
     from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
     unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
@@ -62,6 +65,24 @@ def unet_bench(out):
             out['unet'][f'{mode}_nb{nb}'] = rec
             print('unet', mode, nb, rec, flush=True)
     ops.set_precision('tf32x3')
+
+
+def vae_bench(out):
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    vae = AutoencoderKL().cuda().eval()
+    img = torch.rand(1, 3, 256, 256, device='cuda')
+    z = torch.randn(1, 4, 32, 32, device='cuda')
+    with torch.no_grad():
+        enc = timeit(lambda: vae.encode(img).mode(), iters=10, flush=False)
+        dec = timeit(lambda: vae.decode(z), iters=10, flush=False)
+        vcl = vae.to(memory_format=torch.channels_last)
+        imgc = img.contiguous(memory_format=torch.channels_last)
+        enc_cl = timeit(lambda: vcl.encode(imgc).mode(), iters=10, flush=False)
+        dec_cl = timeit(lambda: vcl.decode(z), iters=10, flush=False)
+    out['vae'] = dict(encode_ms=round(enc, 3), decode_ms=round(dec, 3), encode_cl_ms=round(enc_cl, 3), decode_cl_ms=round(dec_cl, 3))
+    print('vae', out['vae'], flush=True)
 
 
 def render_bench(out):
@@ -92,6 +113,8 @@ def main():
         unet_bench(out)
     if 'render' in sys.argv or len(sys.argv) == 1:
         render_bench(out)
+    if 'vae' in sys.argv or len(sys.argv) == 1:
+        vae_bench(out)
     if len(sys.argv) > 1 and 'conv' not in sys.argv:
         json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
         return
