@@ -43,9 +43,15 @@ WORKLOAD = ('sds_distillation_step: BASELINE configs[2] -- 2 input views, 64 cac
             '128x128 rays x (64+64) samples, PLMS(50), max_thres~U(0,0.99) seeded')
 
 
-def max_thres_sequence(n, seed=1234):
+def max_thres_sequence(warmup, steps, seed=1234):
+    """max_thres of every step (the reference draws U(0,1).clamp(0, .99) per step, distillation.py:303).  Warm-up steps get
+    seeded uniform draws; the K timed steps get a seeded permutation of K equal strata of [0, .99], so that the mean PLMS
+    length of ANY K-step run equals the expectation of the reference's draw instead of depending on K's luck.  The same
+    list is used by the device-resident leg, the end-to-end leg, the reference arm and every rank."""
     g = torch.Generator().manual_seed(seed)
-    return [float(torch.rand(1, generator=g).clamp(0.0, 0.99)) for _ in range(n)]
+    warm = [float(torch.rand(1, generator=g).clamp(0.0, 0.99)) for _ in range(warmup)]
+    order = torch.randperm(steps, generator=g).tolist()
+    return warm + [0.99 * (o + 0.5) / steps for o in order]
 
 
 def peaks():
@@ -135,7 +141,7 @@ def run_gpu(args):
     _lib.load()
     Distiller, nets, scene, kw = build_gpu(rank, world, device)
     K, W = args.steps, args.warmup
-    thres = max_thres_sequence(2 * (K + W) + 8)
+    thres = max_thres_sequence(W, K)
 
     def barrier():
         if world > 1:
@@ -200,8 +206,8 @@ def run_gpu(args):
             a, b = d.step(itr, max_thres=mt)
             return float(a.item()) + float(b.item())   # D2H read of the step's losses (the reference logs loss.item(), :249,:349)
         for i in range(2):
-            step_e2e(dist, 1001 + i, thres[i])
-        ms_e2e = timed(dist, step_e2e, K, W + K)
+            step_e2e(dist, 1001 + i, thres[i % max(1, W)])
+        ms_e2e = timed(dist, step_e2e, K, W)        # same itr numbers and max_thres list as the device-resident leg
         e2e_val, h2d, d2h = world * K / (ms_e2e / 1e3), bytes_per_step[0], 8
 
     # ---- (3) roofline of the dominant kernel: instrumented eager UNet evaluations (CUDA events around every conv launch)
@@ -344,7 +350,7 @@ def run_reference(args):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    thres = max_thres_sequence(2 * (K + W) + 8)
+    thres = max_thres_sequence(W, K)
     calls = [min(int(t * 100), 50) + 1 if t >= 0.01 else 0 for t in thres[W:W + K]]
     per_step = []
     port = CpuPort()

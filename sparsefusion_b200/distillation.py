@@ -43,6 +43,12 @@ def huber(x, y, scaling=0.1):  # utils/common_utils.py:183-190
     return ((1 + diff_sq / (scaling ** 2)).clamp(1e-4).sqrt() - 1) * float(scaling)
 
 
+def shard_target_view(perm: torch.Tensor, rank: int) -> int:
+    """which target view a rank distils this step: entry (1 + rank) of the step's permutation, wrapping (the reference,
+    single process, takes entry 1: distillation.py:264).  Ranks < n_targets therefore get distinct views."""
+    return int(perm[(1 + rank) % perm.numel()])
+
+
 @dataclass
 class SceneCache:
     """what the reference holds per scene before the loop starts (distillation.py:65-125), as device tensors"""
@@ -94,7 +100,16 @@ class FlatAdam:
     def zero_grad(self):
         self.grad.zero_()  # parameters' .grad are views of this buffer; never set them to None
 
+    def sync_grads(self, world_size: int = 1, process_group=None) -> float:
+        """N>1: ONE sum all-reduce of the flat gradient buffer (NCCL over NVLink on the GPU box, gloo in the CPU tests);
+        returns the grad_scale (1/world_size) the following step() must use so that the update is the mean over ranks"""
+        if world_size > 1:
+            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=process_group)
+        return 1.0 / world_size
+
     def step(self, grad_scale: float = 1.0):
+        if not self.flat.is_cuda:
+            raise RuntimeError('FlatAdam.step: the fused Adam kernel needs CUDA parameters (there is no CPU path)')
         self.t += 1
         lr_mult = self.gamma ** (self.sched // self.step_size)
         for start, end, lr in self.groups:
@@ -154,9 +169,8 @@ class Distiller:
         loss = loss + self.lambda_opacity * opacity                                           # :234
         self.optimizer.zero_grad()                                                            # :244
         loss.backward()
-        if self.world_size > 1:  # replicated sub-step: the reduce only removes atomic-order drift so that ranks stay bit-identical
-            torch.distributed.all_reduce(self.optimizer.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        self.optimizer.step(grad_scale=1.0 / self.world_size)
+        # replicated sub-step: for N>1 the reduce only removes atomic-order drift so that ranks stay bit-identical
+        self.optimizer.step(grad_scale=self.optimizer.sync_grads(self.world_size, self.pg))
         self.optimizer.scheduler_step()                                                       # :247
         self.last['photo_loss'] = loss.detach()
         return loss.detach()
@@ -167,7 +181,7 @@ class Distiller:
         self.optimizer.zero_grad()                                                            # :261
         n_t = c.target_features.shape[0]
         perm = torch.randperm(n_t, generator=self.gen)                                        # :263
-        vi = int(perm[(1 + self.rank) % n_t])                                                 # :264
+        vi = shard_target_view(perm, self.rank)                                               # :264
         u = torch.rand(1, generator=self.gen)                                                 # :303 (drawn every step to keep the stream aligned)
         feats = c.target_features[vi:vi + 1]
         image, sil = self._render(c.target_rays_o[vi], c.target_rays_d[vi], 'B')
@@ -191,9 +205,7 @@ class Distiller:
         opacity = torch.sqrt(sil ** 2 + .01).mean()                                           # :336
         loss = fusion_loss + self.lambda_opacity * opacity                                    # :344
         loss.backward()                                                                       # :345
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.optimizer.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        self.optimizer.step(grad_scale=1.0 / self.world_size)                                 # :352
+        self.optimizer.step(grad_scale=self.optimizer.sync_grads(self.world_size, self.pg))   # :352
         self.last['fusion_loss'] = loss.detach()
         return loss.detach()
 
