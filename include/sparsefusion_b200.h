@@ -42,9 +42,12 @@ int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * to TF32 where they are produced; ~1.5e-3 relative error on the UNet output, ~1/3 of the tensor-pipe work. */
 int sfb_set_precision(int mode);
 int sfb_get_precision(void);
-/* experiment switch (default on): every kernel requests the maximum shared-memory carve-out so that consecutive launches never make the SMs
- * re-partition L1 / shared memory.  Only affects kernels launched for the first time after the call. */
-int sfb_set_carveout(int on);
+/* programmatic dependent launch of the UNet kernels (default on): each kernel may be scheduled while its predecessor drains and
+ * waits (griddepcontrol.wait) before touching global memory.  0 restores plain stream-ordered launches (A/B measurement). */
+int sfb_set_pdl(int on);
+/* single-launch fused variants (default all on): bit 0 = cluster GroupNorm (stats + apply in one kernel), bit 1 = cluster global-context
+ * pooling (logits + softmax + pooling in one kernel).  Cleared bits select the multi-kernel paths; results agree to fp32 rounding. */
+int sfb_set_fusion(int mask);
 /* number of kernels this library has launched so far in this process (bench.py's "gpu_launches") */
 uint64_t sfb_launch_count(void);
 

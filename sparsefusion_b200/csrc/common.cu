@@ -37,14 +37,12 @@ static int g_precision = 1;  // 0: single-pass TF32 (operands rounded on write);
 int precision_mode() { return g_precision; }
 void set_precision_mode(int m) { g_precision = m; }
 
-int g_carveout = 1;
-void prefer_smem(const void* kernel) {
-    static std::unordered_set<const void*> done;
-    static std::mutex mu;
-    if (!g_carveout) return;
-    std::lock_guard<std::mutex> lock(mu);
-    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load() != 0; }
+void set_pdl(int on) { g_pdl.store(on != 0); }
+static std::atomic<int> g_fusion{0x7fffffff};
+int fusion_mask() { return g_fusion.load(); }
+void set_fusion_mask(int m) { g_fusion.store(m); }
 
 int sm_count() {
     static int n = 0;
@@ -71,7 +69,8 @@ int sfb_set_precision(int mode) {
     return SFB_OK;
 }
 int sfb_get_precision(void) { return sfb::precision_mode(); }
-int sfb_set_carveout(int on) { sfb::g_carveout = on != 0; return SFB_OK; }
+int sfb_set_pdl(int on) { sfb::set_pdl(on); return SFB_OK; }
+int sfb_set_fusion(int mask) { sfb::set_fusion_mask(mask); return SFB_OK; }
 uint64_t sfb_launch_count(void) { return (uint64_t)sfb::g_launches.load(); }
 
 int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -25,17 +25,49 @@ void count_launches(int n);            // extra launches made under a single che
 int precision_mode();
 void set_precision_mode(int m);
 
-// Every kernel of the library asks for the maximum shared-memory carve-out, whether it needs it or not: the tcgen05 GEMMs use ~200 KB of
-// smem, and alternating them with small-smem kernels would otherwise make the SMs re-partition L1/smem between consecutive launches.
-void prefer_smem(const void* kernel);
-template <typename... A>
-static inline auto kernel_with_carveout(void (*k)(A...)) -> void (*)(A...) {
-    prefer_smem((const void*)k);
-    return k;
+// Programmatic dependent launch (PDL).  The UNet evaluation is ~350 short kernels replayed from one CUDA graph; each of them
+// (a) is launched with programmatic stream serialisation, so its CTAs may become resident while the previous kernel drains, and
+// (b) starts with pdl_sync(): signal that the NEXT kernel may be scheduled, then wait until every kernel before this one has completed
+// and flushed its memory.  All global reads and writes of a kernel come after that wait, so ordering is unchanged.
+bool pdl_enabled();
+// which single-launch fused variants are enabled (sfb_set_fusion): bit 0 GroupNorm cluster kernel, bit 1 global-context pooling cluster kernel
+int fusion_mask();
+static inline bool gn_fused_enabled() { return (fusion_mask() & 1) != 0; }
+static inline bool gca_fused_enabled() { return (fusion_mask() & 2) != 0; }
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
+// cluster_x > 1 launches thread-block clusters of (cluster_x, 1, 1); grid.x must be a multiple of it
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl_cluster(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x,
+                                             A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = 1;
+    if (cluster_x > 1) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cluster_x;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
 }
-}  // namespace sfb
-#define SFB_K(...) sfb::kernel_with_carveout(__VA_ARGS__)
-namespace sfb {
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    return launch_pdl_cluster(kernel, grid, block, smem, st, 1u, static_cast<A&&>(args)...);
+}
+#endif
+
 
 // number of SMs of the current device (cached)
 int sm_count();

@@ -314,7 +314,6 @@ static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
     }
     conv_prof_begin(st);
     void (*kp)(const ConvGemmParams) = conv_gemm_tf32_kernel<BN, NP>;
-    prefer_smem((const void*)kp);
     kp<<<grid, kThreads, ConvCfg<BN, NP>::kSmemBytes, st>>>(p);
     conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32");

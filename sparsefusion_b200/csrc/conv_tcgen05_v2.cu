@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
-            for (int it = 0; it < niter; ++it) {
+            auto load_weights = [&](int it) {
                 const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                tc::mbar_expect_tx(&full_bar[s], kABytes + Cfg::kNBytes);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                tc::tma_load_2d(SWAP ? st : st + kABytes, &p.tmB, &full_bar[s], (kb + it) * kBK, cout0);
+            };
+            auto load_acts = [&](int it) {
+                const int s = it % S;
                 const int i = kb + it;
                 const int tap = i / p.cin_chunks, cc = i - tap * p.cin_chunks;
                 const int ky = tap / p.KW, kx = tap - ky * p.KW;
@@ -113,10 +115,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                     ox = (ox - px) >> 1;
                 }
                 uint8_t* st = smem + s * Cfg::kStageBytes;
-                uint8_t* act_dst = SWAP ? st + kABytes : st;
-                uint8_t* wgt_dst = SWAP ? st : st + kABytes;
-                tc::tma_load_4d(act_dst, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
-                tc::tma_load_2d(wgt_dst, &p.tmB, &full_bar[s], i * kBK, cout0);
+                tc::tma_load_4d(SWAP ? st + kABytes : st, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
+            };
+            // PDL: the weights do not depend on the previous kernel -- the first S stages of weight tiles stream in while it drains;
+            // the activation tiles of those stages follow once griddepcontrol.wait returns.
+            const int pre = niter < S ? niter : S;
+            pdl_trigger();
+            for (int it = 0; it < pre; ++it) {
+                tc::mbar_expect_tx(&full_bar[it], kABytes + Cfg::kNBytes);
+                load_weights(it);
+            }
+            pdl_wait();
+            for (int it = 0; it < pre; ++it) load_acts(it);
+            for (int it = pre; it < niter; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+                tc::mbar_expect_tx(&full_bar[s], kABytes + Cfg::kNBytes);
+                load_acts(it);
+                load_weights(it);
             }
         }
     } else if (warp == 1) {
@@ -152,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             bias_s[i] = (p.bias != nullptr && blockIdx.z == 0 && c < p.Cout) ? p.bias[c] : 0.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        pdl_wait();   // residual reads / output writes below must see the previous kernel's results (bias is a constant)
 
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int it = 0; it < niter; ++it) {
@@ -286,9 +304,7 @@ static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
         configured = true;
     }
     conv_prof_begin(st);
-    void (*kp)(const ConvGemmParams) = conv_gemm_v2_kernel<BN, SWAP>;
-    prefer_smem((const void*)kp);
-    kp<<<grid, kThreads, Conv2Cfg<BN>::kSmemBytes, st>>>(p);
+    launch_pdl(conv_gemm_v2_kernel<BN, SWAP>, grid, dim3(kThreads), Conv2Cfg<BN>::kSmemBytes, st, p);
     conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32(v2)");
 }

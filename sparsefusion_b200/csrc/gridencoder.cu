@@ -193,7 +193,7 @@ template <uint32_t D, uint32_t C>
 static int launch_forward(const float* inputs, const float* emb, const int32_t* offsets, float* out, uint32_t B, uint32_t L, float S,
                           uint32_t H, float* dy_dx, uint32_t gridtype, bool ac, cudaStream_t st) {
     dim3 grid(ceil_div(B, 256u), L);
-    SFB_K(grid_forward_kernel<D, C>)<<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac);
+    grid_forward_kernel<D, C><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac);
     return check_launch("grid_encode_forward");
 }
 
@@ -201,10 +201,10 @@ template <uint32_t D, uint32_t C>
 static int launch_backward(const float* grad, const float* inputs, const int32_t* offsets, float* ge, uint32_t B, uint32_t L, float S,
                            uint32_t H, const float* dy_dx, float* gi, uint32_t gridtype, bool ac, cudaStream_t st) {
     dim3 grid(ceil_div(B, 256u), L);
-    SFB_K(grid_backward_kernel<D, C>)<<<grid, 256, 0, st>>>(grad, inputs, offsets, ge, B, L, S, H, gridtype, ac);
+    grid_backward_kernel<D, C><<<grid, 256, 0, st>>>(grad, inputs, offsets, ge, B, L, S, H, gridtype, ac);
     if (int rc = check_launch("grid_encode_backward")) return rc;
     if (dy_dx && gi) {
-        SFB_K(grid_input_backward_kernel<D, C>)<<<ceil_div(B * D, 256u), 256, 0, st>>>(grad, dy_dx, gi, B, L);
+        grid_input_backward_kernel<D, C><<<ceil_div(B * D, 256u), 256, 0, st>>>(grad, dy_dx, gi, B, L);
         return check_launch("grid_encode_backward(inputs)");
     }
     return SFB_OK;
@@ -256,7 +256,7 @@ int sfb_grid_encode_backward(const float* grad, const float* inputs, const float
 
 int sfb_grid_level_scales(uint32_t L, float S, uint32_t H, float* scales, void* stream) {
     SFB_REQUIRE(scales && L <= 32, "grid_level_scales: null pointer or L > 32");
-    SFB_K(grid_scales_kernel)<<<1, 32, 0, as_stream(stream)>>>(L, S, H, scales);
+    grid_scales_kernel<<<1, 32, 0, as_stream(stream)>>>(L, S, H, scales);
     return check_launch("grid_level_scales");
 }
 
@@ -267,8 +267,8 @@ int sfb_grid_corner_rows(const float* inputs, const int32_t* offsets, int32_t* r
     dim3 grid(ceil_div(B, 256u), L);
     cudaStream_t st = as_stream(stream);
     switch (D) {
-        case 2: SFB_K(grid_rows_kernel<2>)<<<grid, 256, 0, st>>>(inputs, offsets, rows, B, L, S, H, gridtype, align_corners != 0); break;
-        case 3: SFB_K(grid_rows_kernel<3>)<<<grid, 256, 0, st>>>(inputs, offsets, rows, B, L, S, H, gridtype, align_corners != 0); break;
+        case 2: grid_rows_kernel<2><<<grid, 256, 0, st>>>(inputs, offsets, rows, B, L, S, H, gridtype, align_corners != 0); break;
+        case 3: grid_rows_kernel<3><<<grid, 256, 0, st>>>(inputs, offsets, rows, B, L, S, H, gridtype, align_corners != 0); break;
         default: return fail(SFB_ERR_ARG, "grid_corner_rows: D must be 2 or 3");
     }
     return check_launch("grid_corner_rows");

@@ -408,7 +408,7 @@ int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* ra
     static bool cfg = false;
     if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
     const uint32_t blocks = min(ceil_div(B, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 3);
-    SFB_K(field_forward_kernel)<<<blocks, kFieldThreads, smem, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
+    field_forward_kernel<<<blocks, kFieldThreads, smem, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
                                                                             FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, sigma, rgb);
     return check_launch("ngp_field_forward");
 }
@@ -438,14 +438,14 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
     if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
     cudaStream_t st = as_stream(stream);
     const uint32_t blocks = min(ceil_div(Bp, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 2);
-    SFB_K(field_backward_kernel)<<<blocks, kFieldThreads, smem, st>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, Bp, embeddings, offsets,
+    field_backward_kernel<<<blocks, kFieldThreads, smem, st>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, Bp, embeddings, offsets,
                                                               FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, grad_sigma, grad_rgb,
                                                               grad_embeddings, H0, H1, H2, D1, D2, D3);
     if (int rc = check_launch("ngp_field_backward(data)")) return rc;
     const uint32_t wb = min(Bp / 64, (uint32_t)sm_count() * 2);
-    SFB_K(mlp_wgrad_kernel<kHid, kIn>)<<<wb, 256, 0, st>>>(D1, H0, Bp, gW0, gb0);
-    SFB_K(mlp_wgrad_kernel<kHid, kHid>)<<<wb, 256, 0, st>>>(D2, H1, Bp, gW1, gb1);
-    SFB_K(mlp_wgrad_kernel<kOut, kHid>)<<<wb, 256, 0, st>>>(D3, H2, Bp, gW2, gb2);
+    mlp_wgrad_kernel<kHid, kIn><<<wb, 256, 0, st>>>(D1, H0, Bp, gW0, gb0);
+    mlp_wgrad_kernel<kHid, kHid><<<wb, 256, 0, st>>>(D2, H1, Bp, gW1, gb1);
+    mlp_wgrad_kernel<kOut, kHid><<<wb, 256, 0, st>>>(D3, H2, Bp, gW2, gb2);
     count_launches(2);
     return check_launch("ngp_field_backward(weights)");
 }
@@ -462,7 +462,7 @@ int sfb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-    SFB_K(adam_kernel)<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
+    adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
     return check_launch("adam_step");
 }
 }

@@ -280,7 +280,7 @@ int sfb_ray_coarse_z(const float* rays_o, const float* rays_d, const float* aabb
     if (N == 0) return SFB_OK;
     SFB_REQUIRE(rays_o && rays_d && aabb && lin && nears && fars && z, "ray_coarse_z: null pointer");
     SFB_REQUIRE(num_steps == (uint32_t)kTc, "ray_coarse_z: the fused renderer is built for num_steps == 64 (get_default_torch_ngp_opt)");
-    SFB_K(ray_coarse_z_kernel)<<<ceil_div(N * (uint32_t)kTc, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, min_near, lin, noise, N, nears, fars, z);
+    ray_coarse_z_kernel<<<ceil_div(N * (uint32_t)kTc, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, min_near, lin, noise, N, nears, fars, z);
     return check_launch("ray_coarse_z");
 }
 
@@ -289,7 +289,7 @@ int sfb_ray_resample(const float* z_coarse, const float* sigma_coarse, const flo
     if (N == 0) return SFB_OK;
     SFB_REQUIRE(z_coarse && sigma_coarse && nears && fars && z_sorted && (det || u), "ray_resample: null pointer");
     SFB_REQUIRE(num_steps == (uint32_t)kTc && upsample_steps == (uint32_t)kTf, "ray_resample: built for 64 + 64 samples per ray");
-    SFB_K(ray_resample_kernel)<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_coarse, sigma_coarse, nears, fars, u, det,
+    ray_resample_kernel<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_coarse, sigma_coarse, nears, fars, u, det,
                                                                                                           N, z_sorted);
     return check_launch("ray_resample");
 }
@@ -299,7 +299,7 @@ int sfb_ray_composite_forward(const float* z_sorted, const float* sigma, const f
     if (N == 0) return SFB_OK;
     SFB_REQUIRE(z_sorted && sigma && rgb && nears && fars && image && depth && weights_sum, "ray_composite_forward: null pointer");
     SFB_REQUIRE(T == (uint32_t)kT, "ray_composite_forward: built for 128 samples per ray");
-    SFB_K(ray_composite_kernel)<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_sorted, sigma, rgb, nears, fars, bg_color,
+    ray_composite_kernel<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_sorted, sigma, rgb, nears, fars, bg_color,
                                                                                                            N, image, depth, weights_sum);
     return check_launch("ray_composite_forward");
 }
@@ -310,7 +310,7 @@ int sfb_ray_composite_backward(const float* z_sorted, const float* sigma, const 
     if (N == 0) return SFB_OK;
     SFB_REQUIRE(z_sorted && sigma && rgb && nears && fars && grad_image && grad_sigma && grad_rgb, "ray_composite_backward: null pointer");
     SFB_REQUIRE(T == (uint32_t)kT, "ray_composite_backward: built for 128 samples per ray");
-    SFB_K(ray_composite_bwd_kernel)<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
+    ray_composite_bwd_kernel<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
         z_sorted, sigma, rgb, nears, fars, bg_color, N, grad_image, grad_weights_sum, grad_depth, grad_sigma, grad_rgb);
     return check_launch("ray_composite_backward");
 }

@@ -273,28 +273,28 @@ int sfb_near_far_from_aabb(const float* rays_o, const float* rays_d, const float
                            float* fars, void* stream) {
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(rays_o && rays_d && aabb && nears && fars, "near_far_from_aabb: null pointer");
-    SFB_K(near_far_kernel)<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    near_far_kernel<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
     return check_launch("near_far_from_aabb");
 }
 
 int sfb_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream) {
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(rays_o && rays_d && coords, "sph_from_ray: null pointer");
-    SFB_K(sph_from_ray_kernel)<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
+    sph_from_ray_kernel<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
     return check_launch("sph_from_ray");
 }
 
 int sfb_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(coords && indices, "morton3D: null pointer");
-    SFB_K(morton3D_kernel)<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(coords, N, indices);
+    morton3D_kernel<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(coords, N, indices);
     return check_launch("morton3D");
 }
 
 int sfb_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(coords && indices, "morton3D_invert: null pointer");
-    SFB_K(morton3D_invert_kernel)<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(indices, N, coords);
+    morton3D_invert_kernel<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(indices, N, coords);
     return check_launch("morton3D_invert");
 }
 
@@ -302,7 +302,7 @@ int sfb_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(grid && bitfield, "packbits: null pointer");
     SFB_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0, "packbits: grid must be 16-byte aligned");
-    SFB_K(packbits_kernel)<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(grid, N, density_thresh, bitfield);
+    packbits_kernel<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(grid, N, density_thresh, bitfield);
     return check_launch("packbits");
 }
 
@@ -312,7 +312,7 @@ int sfb_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter && noises, "march_rays_train: null pointer");
     SFB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024, "march_rays_train: cascade/grid size out of range");
-    SFB_K(march_rays_train_kernel)<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+    march_rays_train_kernel<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
                                                                              fars, xyzs, dirs, deltas, rays, counter, noises);
     return check_launch("march_rays_train");
 }
@@ -321,7 +321,7 @@ int sfb_composite_rays_train_forward(const float* sigmas, const float* rgbs, con
                                      float T_thresh, float* weights_sum, float* depth, float* image, void* stream) {
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image, "composite_rays_train_forward: null pointer");
-    SFB_K(composite_train_fwd_kernel)<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    composite_train_fwd_kernel<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
     return check_launch("composite_rays_train_forward");
 }
 
@@ -331,7 +331,7 @@ int sfb_composite_rays_train_backward(const float* grad_weights_sum, const float
     if (N == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image && grad_sigmas && grad_rgbs,
                 "composite_rays_train_backward: null pointer");
-    SFB_K(composite_train_bwd_kernel)<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+    composite_train_bwd_kernel<<<ceil_div(N, 128u), 128, 0, as_stream(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
                                                                                 weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
     return check_launch("composite_rays_train_backward");
 }
@@ -341,7 +341,7 @@ int sfb_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
                    const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises, void* stream) {
     if (n_alive == 0 || n_step == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && noises, "march_rays: null pointer");
-    SFB_K(march_rays_kernel)<<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+    march_rays_kernel<<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
                                                                              max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises);
     return check_launch("march_rays");
 }
@@ -350,7 +350,7 @@ int sfb_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
                        const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image, void* stream) {
     if (n_alive == 0) return SFB_OK;  // empty problem: nothing to do, pointers may be null
     SFB_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "composite_rays: null pointer");
-    SFB_K(composite_rays_kernel)<<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
+    composite_rays_kernel<<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
                                                                                  deltas, weights_sum, depth, image);
     return check_launch("composite_rays");
 }

@@ -9,6 +9,7 @@
 // streaming GEMVs and stay in full fp32.
 // Tensors that feed a tcgen05 GEMM are rounded to TF32 (cvt.rna) when they are written here, so the
 // tensor core's operand truncation never biases the result.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include "../../include/sparsefusion_b200.h"
@@ -38,6 +39,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // ------------------------------------------------------------------------------------ layout
 // NCHW [NB,C,H,W] -> channel slice [c_off, c_off+C) of NHWC [NB,H,W,ld]; 32x32 smem transpose per (n)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int64_t ld, int c_off, int round) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -57,6 +59,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
     }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int64_t ld) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -75,6 +78,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
 // out[pix][0:C1] = a[pix][0:C1]; out[pix][C1:C1+C2] = b[pix][0:C2] * scale_b   (float4 granularity)
 __global__ void concat2_kernel(const float4* __restrict__ a, int C1v, int64_t lda_v, const float4* __restrict__ b, int C2v, int64_t ldb_v,
                                float scale_b, float4* __restrict__ out, int64_t ldo_v, int64_t npix) {
+    pdl_sync();
     const int Cv = C1v + C2v;
     const int64_t total = npix * Cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -92,6 +96,7 @@ __global__ void concat2_kernel(const float4* __restrict__ a, int C1v, int64_t ld
 
 // PixelShuffle(2) of silu(y): y [NB,H,W,4*Co] -> out [NB,2H,2W, channel slice of width Co]; y channel = c*4 + i*2 + j
 __global__ void pixel_shuffle_silu_kernel(const float* __restrict__ y, float* __restrict__ out, int H, int W, int Co, int64_t ldo, int64_t total) {
+    pdl_sync();
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         // idx enumerates output elements: ((n*2H + oh)*2W + ow)*Co + c
         const int c = (int)(idx % Co);
@@ -111,6 +116,7 @@ __global__ void pixel_shuffle_silu_kernel(const float* __restrict__ y, float* __
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps, int S,
                                                       double2* __restrict__ partial, unsigned int* __restrict__ counters,
                                                       float2* __restrict__ stats) {
+    pdl_sync();
     const int g = blockIdx.x, n = blockIdx.y, sl = blockIdx.z;
     const int Cg = C / G;
     const int Cg4 = Cg >> 2;
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const float2* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
                                 int G, int act, int round, int64_t total4) {
+    pdl_sync();
     const int C4 = C >> 2, Cg = C / G;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = i / C4;
@@ -193,6 +200,92 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const 
     }
 }
 
+// Single-launch GroupNorm for the sizes of a B<=8 UNet evaluation: one thread-block CLUSTER per (n, group), CTA r of the cluster owns a
+// slab of pixels, keeps its <= 8 float4 per thread in registers, publishes fp64 (sum, sumsq) in shared memory, reads the other CTAs'
+// partials through distributed shared memory and applies affine / FiLM / SiLU straight from the registers -- x is read once.
+constexpr int kGnFusedItems = 8;   // float4 per thread
+__global__ void __launch_bounds__(256) gn_fused_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int act,
+                                                       int round) {
+    pdl_sync();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int R = (int)gridDim.x, sl = (int)blockIdx.x, g = blockIdx.y, n = blockIdx.z;
+    const int Cg = C / G, Cg4 = Cg >> 2;
+    const int p0 = (int)(((int64_t)HW * sl) / R), p1 = (int)(((int64_t)HW * (sl + 1)) / R);
+    const int total4 = (p1 - p0) * Cg4;
+    const float* base = x + ((int64_t)n * HW + p0) * ldx + g * Cg;
+    float4 v[kGnFusedItems];
+    double s = 0.0, ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < kGnFusedItems; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < total4) {
+            const int pix = i / Cg4, c4 = i - pix * Cg4;
+            v[k] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * ldx) + c4);
+            s += (double)(v[k].x + v[k].y + v[k].z + v[k].w);
+            ss += (double)(v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w);
+        }
+    }
+    __shared__ double sh_s[8], sh_ss[8];
+    __shared__ double part[2];
+    __shared__ float2 st_sh;
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh_s[w]; b += sh_ss[w]; }
+        part[0] = a; part[1] = b;
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tss = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const double* rp = cluster.map_shared_rank(part, r);
+            ts += rp[0]; tss += rp[1];
+        }
+        const double cnt = (double)HW * Cg;
+        const double mean = ts / cnt;
+        double var = tss / cnt - mean * mean;
+        if (var < 0) var = 0;
+        st_sh = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    cluster.sync();   // also keeps every CTA's `part` alive until all remote reads are done
+    const float2 st = st_sh;
+    float* ybase = y + ((int64_t)n * HW + p0) * ldy + g * Cg;
+#pragma unroll
+    for (int k = 0; k < kGnFusedItems; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < total4) {
+            const int pix = i / Cg4, c4 = i - pix * Cg4;
+            const int c = g * Cg + c4 * 4;
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float o[4] = {(v[k].x - st.x) * st.y * ga.x + be.x, (v[k].y - st.x) * st.y * ga.y + be.y, (v[k].z - st.x) * st.y * ga.z + be.z,
+                          (v[k].w - st.x) * st.y * ga.w + be.w};
+            if (film) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + c));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + C + c));
+                o[0] = o[0] * (sc.x + 1.f) + sh.x; o[1] = o[1] * (sc.y + 1.f) + sh.y;
+                o[2] = o[2] * (sc.z + 1.f) + sh.z; o[3] = o[3] * (sc.w + 1.f) + sh.w;
+            }
+            if (act) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
+            }
+            if (round) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = tc::round_tf32(o[e]);
+            }
+            *(reinterpret_cast<float4*>(ybase + (int64_t)pix * ldy) + c4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ LayerNorm over the last dim
 // rows [T, C] (row stride ldx); y = LN(pre(x)) * g (+ b) (+ res); pre: 0 none, 1 GELU.  One 128-thread CTA per row.  eps 1e-5, biased variance.
 __device__ __forceinline__ float block_sum_128(float v, float* sh) {
@@ -206,6 +299,7 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh) {
 __global__ void __launch_bounds__(128) layernorm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
                                                             const float* __restrict__ b, const float* __restrict__ res, int64_t ldr,
                                                             float* __restrict__ y, int64_t ldy, int T, int C, int pre, int round) {
+    pdl_sync();
     __shared__ float sh[4];
     const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * ldx;
@@ -242,6 +336,7 @@ template <int MT>
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ Wt,
                                                           const float* __restrict__ bias, const float* __restrict__ res, int64_t ldr,
                                                           float* __restrict__ y, int64_t ldy, int M, int K, int O, int pre, int post, int round) {
+    pdl_sync();
     extern __shared__ float xs[];  // [MT][K]
     const int m0 = blockIdx.y * MT;
     const int mrows = min(MT, M - m0);
@@ -293,6 +388,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
 // ------------------------------------------------------------------------------------ time embedding
 // four[b] = [t, sin(2 pi t w_0..), cos(2 pi t w_0..)]   (imagen_pytorch.py:634-639)
 __global__ void time_fourier_kernel(const float* __restrict__ t, const float* __restrict__ w, float* __restrict__ out, int B, int half) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int width = 2 * half + 1;
     if (i >= B * width) return;
@@ -314,6 +410,7 @@ __global__ void time_fourier_kernel(const float* __restrict__ t, const float* __
 // One warp per (b, head, query); dh <= 128.
 __global__ void mq_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ null_kv,
                                     const float* __restrict__ ckv, float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale, int round) {
+    pdl_sync();
     extern __shared__ float sm[];  // per warp: scores[nk]
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * warps + warp;
@@ -352,6 +449,7 @@ __global__ void mq_attention_kernel(const float* __restrict__ q, const float* __
 // null_kv [2,dh] shared by heads; keys: null, context.  One warp per (b, head, query).
 __global__ void cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const float* __restrict__ null_kv,
                                        float* __restrict__ out, int B, int n, int heads, int dh, int nc, float scale, int round) {
+    pdl_sync();
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * warps + warp;
     if (gw >= B * heads * n) return;
@@ -386,6 +484,7 @@ __global__ void cross_attention_kernel(const float* __restrict__ q, const float*
 // logits[n][p] = bias + sum_c x[n][p][c] * wk[c]      (to_k, imagen_pytorch.py:926,937) -- one warp per pixel
 __global__ void gca_logits_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ wk, const float* __restrict__ bk,
                                   float* __restrict__ logits, int64_t npix, int C) {
+    pdl_sync();
     const int64_t p = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= npix) return;
     const int lane = threadIdx.x & 31;
@@ -402,6 +501,7 @@ __global__ void gca_logits_kernel(const float* __restrict__ x, int64_t ldx, cons
 // softmax statistics of one image's logits -> stat[n] = (max, 1/sum exp); also zeroes pooled[n][:] for the accumulation pass
 __global__ void __launch_bounds__(256) gca_stats_kernel(const float* __restrict__ logits, float2* __restrict__ stat, float* __restrict__ pooled,
                                                        int HW, int C) {
+    pdl_sync();
     __shared__ float red[8];
     const int n = blockIdx.x;
     const float* lg = logits + (int64_t)n * HW;
@@ -428,6 +528,7 @@ __global__ void __launch_bounds__(256) gca_stats_kernel(const float* __restrict_
 // pooled[n][c] += sum_{p in slab} softmax(logits)[p] * x[n][p][c]      grid (slabs of 16 pixels, NB), threads = channels
 __global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
                                                       const float2* __restrict__ stat, float* __restrict__ pooled, int HW, int C) {
+    pdl_sync();
     constexpr int SLAB = 16;
     __shared__ float wts[SLAB];
     const int n = blockIdx.y, p0 = blockIdx.x * SLAB;
@@ -444,9 +545,106 @@ __global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__
     }
 }
 
+// Single-launch GlobalContext pooling: one cluster of R CTAs per image, CTA r owns a slab of pixels.  Per CTA: logits of its pixels (warp per
+// pixel), slab-local softmax statistics (m_r, l_r) and the slab-local weighted channel sums P_r[c] = sum_p exp(logit_p - m_r) x[p][c]; after a
+// cluster barrier CTA r combines channel slice r of all slabs through distributed shared memory:
+//   pooled[c] = sum_r e^{m_r - m} P_r[c] / sum_r e^{m_r - m} l_r,   m = max_r m_r            (the flash-attention merge; C <= 1024, slab <= 256 px)
+constexpr int kGcaMaxC = 1024, kGcaMaxSlab = 256;
+__global__ void __launch_bounds__(256) gca_fused_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ wk,
+                                                       const float* __restrict__ bk, float* __restrict__ pooled, int HW, int C) {
+    pdl_sync();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float wts[kGcaMaxSlab];
+    __shared__ __align__(16) float part[1024];
+    __shared__ __align__(16) float pp[kGcaMaxC];
+    __shared__ float red[8];
+    __shared__ float ml[2];
+    const int R = (int)gridDim.x, sl = (int)blockIdx.x, n = blockIdx.y;
+    const int p0 = (int)(((int64_t)HW * sl) / R), p1 = (int)(((int64_t)HW * (sl + 1)) / R);
+    const int np = p1 - p0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xb = x + ((int64_t)n * HW + p0) * ldx;
+    const float b0 = __ldg(bk);
+    // (1) logits
+    for (int p = warp; p < np; p += 8) {
+        const float* xr = xb + (int64_t)p * ldx;
+        float d = 0.f;
+        for (int c = lane * 4; c < C; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wk + c));
+            d += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+        }
+        d = warp_sum(d);
+        if (lane == 0) wts[p] = d + b0;
+    }
+    __syncthreads();
+    // (2) slab-local max and exp-sum; wts <- exp(logit - m_r)
+    float mx = -INFINITY;
+    for (int p = threadIdx.x; p < np; p += 256) mx = fmaxf(mx, wts[p]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sm = 0.f;
+    for (int p = threadIdx.x; p < np; p += 256) {
+        const float e = __expf(wts[p] - mx);
+        wts[p] = e;
+        sm += e;
+    }
+    sm = warp_sum(sm);
+    if (lane == 0) red[warp] = sm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        ml[0] = mx; ml[1] = t;
+    }
+    // (3) P_r[c]: thread = (pixel group, float4 column); groups split the slab's pixels, then fold through shared memory
+    const int ncol = C >> 2;                       // <= 256
+    const int ngrp = 256 / ncol;                   // >= 1
+    const int grp = threadIdx.x / ncol, col = threadIdx.x - grp * ncol;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grp < ngrp) {
+#pragma unroll 4
+        for (int p = grp; p < np; p += ngrp) {
+            const float w = wts[p];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)p * ldx) + col);
+            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+        reinterpret_cast<float4*>(part)[grp * ncol + col] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int g = 0; g < ngrp; ++g) t += part[g * C + c];
+        pp[c] = t;
+    }
+    cluster.sync();
+    // (4) merge channel slice `sl` across the cluster's slabs
+    float m = -INFINITY;
+    for (int r = 0; r < R; ++r) m = fmaxf(m, cluster.map_shared_rank(ml, r)[0]);
+    float den = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const float* rml = cluster.map_shared_rank(ml, r);
+        den += __expf(rml[0] - m) * rml[1];
+    }
+    const int c0 = (int)(((int64_t)C * sl) / R), c1 = (int)(((int64_t)C * (sl + 1)) / R);
+    for (int c = c0 + threadIdx.x; c < c1; c += 256) {
+        float t = 0.f;
+        for (int r = 0; r < R; ++r) t += __expf(cluster.map_shared_rank(ml, r)[0] - m) * cluster.map_shared_rank(pp, r)[c];
+        pooled[(int64_t)n * C + c] = t / den;
+    }
+    cluster.sync();   // keep this CTA's shared memory alive until every remote read is done
+}
+
 // out = h * gate[n][c] + res      (ResnetBlock tail, imagen_pytorch.py:727-729); gate may be null (== 1)
 __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v, const float* __restrict__ gate, const float4* __restrict__ res,
                                      int64_t ldr_v, float4* __restrict__ out, int64_t ldo_v, int HW, int Cv, int64_t total) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = i / Cv;
         const int c = (int)(i - pix * Cv);
@@ -476,14 +674,14 @@ extern "C" {
 int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream) {
     SFB_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    SFB_K(nchw_to_nhwc_kernel)<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
+    launch_pdl(nchw_to_nhwc_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
     return check_launch("nchw_to_nhwc");
 }
 
 int sfb_nhwc_to_nchw(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, void* stream) {
     SFB_REQUIRE(src && dst, "nhwc_to_nchw: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    SFB_K(nhwc_to_nchw_kernel)<<<grid, block, 0, as_stream(stream)>>>(src, dst, C, H * W, ld);
+    launch_pdl(nhwc_to_nchw_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld);
     return check_launch("nhwc_to_nchw");
 }
 
@@ -492,7 +690,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
     SFB_REQUIRE(a && b && out, "concat2_nhwc: null pointer");
     SFB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0, "concat2_nhwc: channel counts must be multiples of 4");
     const int64_t total = npix * ((C1 + C2) / 4);
-    SFB_K(concat2_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
+    launch_pdl(concat2_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
                                                                     reinterpret_cast<const float4*>(b), C2 / 4, ldb / 4, scale_b,
                                                                     reinterpret_cast<float4*>(out), ldo / 4, npix);
     return check_launch("concat2_nhwc");
@@ -501,7 +699,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream) {
     SFB_REQUIRE(y && out, "pixel_shuffle_silu: null pointer");
     const int64_t total = (int64_t)NB * 4 * H * W * Co;
-    SFB_K(pixel_shuffle_silu_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(y, out, H, W, Co, ldo, total);
+    launch_pdl(pixel_shuffle_silu_kernel, ew_blocks(total), 256, 0, as_stream(stream), y, out, H, W, Co, ldo, total);
     return check_launch("pixel_shuffle_silu");
 }
 
@@ -513,16 +711,27 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     SFB_REQUIRE(((uintptr_t)stats_ws & 15) == 0, "groupnorm_nhwc: workspace must be 16-byte aligned");
     SFB_REQUIRE(C % G == 0 && (C / G) % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "groupnorm_nhwc: channels per group must be a multiple of 4");
     cudaStream_t st = as_stream(stream);
+    {   // single-launch cluster path: the (n, group) slab split over R <= 8 CTAs must fit 8 float4 per thread
+        const int64_t group4 = (int64_t)HW * (C / G / 4);
+        int R = 1;
+        while (R < 8 && (group4 + R - 1) / R > 256 * kGnFusedItems) R *= 2;
+        const bool fits = (((int64_t)HW + R - 1) / R) * (C / G / 4) <= 256 * kGnFusedItems && HW >= R && NB <= 65535;
+        if (fits && gn_fused_enabled()) {
+            launch_pdl_cluster(gn_fused_kernel, dim3(R, G, NB), dim3(256), 0, st, (unsigned)R, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy,
+                               act_silu, (int)(precision_mode() == 0));
+            return check_launch("groupnorm_nhwc(fused)");
+        }
+    }
     // workspace: [0, 2*NB*G) floats = (mean, rstd); then 16-byte aligned fp64 partials [NB*G*S][2]
     int S = 1;
     while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
     float2* stats = reinterpret_cast<float2*>(stats_ws);
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
     SFB_REQUIRE(counters != nullptr, "groupnorm_nhwc: counters workspace is null");
-    SFB_K(gn_stats_kernel)<<<dim3(G, NB, S), 256, 0, st>>>(x, ldx, HW, C, G, eps, S, partial, counters, stats);
+    launch_pdl(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, eps, S, partial, counters, stats);
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t total4 = (int64_t)NB * HW * (C / 4);
-    SFB_K(gn_apply_kernel)<<<ew_blocks(total4), 256, 0, st>>>(x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
+    launch_pdl(gn_apply_kernel, ew_blocks(total4), 256, 0, st, x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
                                                       act_silu, precision_mode() == 0, total4);
     return check_launch("groupnorm_nhwc(apply)");
 }
@@ -530,7 +739,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
                        int C, int pre_gelu, int round_tf32, void* stream) {
     SFB_REQUIRE(x && g && y, "layernorm_rows: null pointer");
-    SFB_K(layernorm_rows_kernel)<<<T, 128, 0, as_stream(stream)>>>(x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
+    launch_pdl(layernorm_rows_kernel, T, 128, 0, as_stream(stream), x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
     return check_launch("layernorm_rows");
 }
 
@@ -543,13 +752,13 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
         const size_t sm = (size_t)2 * K * 4;
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)); cfg = true; }
-        SFB_K(linear_small_kernel<2>)<<<dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        launch_pdl(linear_small_kernel<2>, dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     } else {
         const size_t sm = (size_t)8 * K * 4;
         SFB_REQUIRE(sm <= 200 * 1024, "linear_small: K too large for 8-row tile");
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-        SFB_K(linear_small_kernel<8>)<<<dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st>>>(x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        launch_pdl(linear_small_kernel<8>, dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     }
     return check_launch("linear_small");
 }
@@ -557,7 +766,7 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
 int sfb_time_fourier(const float* t, const float* w, float* out, int B, int half, void* stream) {
     SFB_REQUIRE(t && w && out, "time_fourier: null pointer");
     const int total = B * (2 * half + 1);
-    SFB_K(time_fourier_kernel)<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(t, w, out, B, half);
+    launch_pdl(time_fourier_kernel, ceil_div(total, 128), 128, 0, as_stream(stream), t, w, out, B, half);
     return check_launch("time_fourier");
 }
 
@@ -568,7 +777,7 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
     const int warps = 4;
     const size_t sm = (size_t)warps * nk * 4;
     SFB_REQUIRE(sm <= 48 * 1024, "mq_attention: too many keys for the single-pass kernel");
-    SFB_K(mq_attention_kernel)<<<ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream)>>>(q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    launch_pdl(mq_attention_kernel, ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream), q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("mq_attention");
 }
 
@@ -576,7 +785,7 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
                         void* stream) {
     SFB_REQUIRE(q && kvc && null_kv && out, "cross_attention: null pointer");
     SFB_REQUIRE(nc <= 8, "cross_attention: at most 8 context tokens");
-    SFB_K(cross_attention_kernel)<<<ceil_div(B * heads * n, 4), 128, 0, as_stream(stream)>>>(q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    launch_pdl(cross_attention_kernel, ceil_div(B * heads * n, 4), 128, 0, as_stream(stream), q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("cross_attention");
 }
 
@@ -586,13 +795,19 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0, "gca_pool: unsupported shape");
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)NB * HW;
-    SFB_K(gca_logits_kernel)<<<(unsigned)ceil_div(npix, (int64_t)8), 256, 0, st>>>(x, ldx, wk, bk, logits_ws, npix, C);
+    if (gca_fused_enabled() && C <= kGcaMaxC && 1024 % C == 0 && HW <= 8 * kGcaMaxSlab && NB <= 65535) {
+        int R = 8;
+        while (R > 1 && R > HW) R >>= 1;
+        launch_pdl_cluster(gca_fused_kernel, dim3(R, NB), dim3(256), 0, st, (unsigned)R, x, ldx, wk, bk, pooled, HW, C);
+        return check_launch("gca_pool(fused)");
+    }
+    launch_pdl(gca_logits_kernel, (unsigned)ceil_div(npix, (int64_t)8), 256, 0, st, x, ldx, wk, bk, logits_ws, npix, C);
     if (int rc = check_launch("gca_pool(logits)")) return rc;
     // logits_ws: NB*HW logits followed by NB (max, 1/sum) pairs
     float2* stat = reinterpret_cast<float2*>(logits_ws + ((npix + 1) / 2) * 2);
-    SFB_K(gca_stats_kernel)<<<NB, 256, 0, st>>>(logits_ws, stat, pooled, HW, C);
+    launch_pdl(gca_stats_kernel, NB, 256, 0, st, logits_ws, stat, pooled, HW, C);
     if (int rc = check_launch("gca_pool(stats)")) return rc;
-    SFB_K(gca_pool_kernel)<<<dim3(ceil_div(HW, 16), NB), 256, 0, st>>>(x, ldx, logits_ws, stat, pooled, HW, C);
+    launch_pdl(gca_pool_kernel, dim3(ceil_div(HW, 16), NB), 256, 0, st, x, ldx, logits_ws, stat, pooled, HW, C);
     return check_launch("gca_pool(pool)");
 }
 
@@ -601,7 +816,7 @@ int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const
     SFB_REQUIRE(h && res && out, "gate_residual: null pointer");
     SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0, "gate_residual: channel counts must be multiples of 4");
     const int64_t total = (int64_t)NB * HW * (C / 4);
-    SFB_K(gate_residual_kernel)<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(h), ldh / 4, gate,
+    launch_pdl(gate_residual_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(h), ldh / 4, gate,
                                                                           reinterpret_cast<const float4*>(res), ldr / 4,
                                                                           reinterpret_cast<float4*>(out), ldo / 4, HW, C / 4, total);
     return check_launch("gate_residual");
@@ -619,6 +834,7 @@ __global__ void plms_update_kernel(const float* __restrict__ x, const float* __r
                                    const float* __restrict__ e2, const float* __restrict__ e3, float c0, float c1, float c2, float c3,
                                    const float* __restrict__ noise, float alpha, float sigma, float alpha_next, float c, float noise_scale,
                                    float clip, float* __restrict__ x_prev, float* __restrict__ x0_out, float* __restrict__ e_out, int64_t n) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float e = c0 * e0[i];
         if (e1) e += c1 * e1[i];
@@ -642,7 +858,7 @@ extern "C" int sfb_plms_update(const float* x, const float* e0, const float* e1,
     SFB_REQUIRE(x && e0 && noise && x_prev, "plms_update: null pointer");
     int64_t blocks = (n + 255) / 256;
     if (blocks > 1024) blocks = 1024;
-    SFB_K(sfb::plms_update_kernel)<<<(unsigned)blocks, 256, 0, sfb::as_stream(stream)>>>(x, e0, e1, e2, e3, c0, c1, c2, c3, noise, alpha, sigma, alpha_next, c,
+    sfb::launch_pdl(sfb::plms_update_kernel, (unsigned)blocks, 256, 0, sfb::as_stream(stream), x, e0, e1, e2, e3, c0, c1, c2, c3, noise, alpha, sigma, alpha_next, c,
                                                                                  noise_scale, clip, x_prev, x0_out, e_out, n);
     return sfb::check_launch("plms_update");
 }

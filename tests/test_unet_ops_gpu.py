@@ -36,9 +36,19 @@ def test_pixel_shuffle_silu():
     _close(ops.pixel_shuffle_silu(y), ref, 1e-5)
 
 
-@pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8)])
+@pytest.fixture(params=[0x7fffffff, 0], ids=['fused', 'multikernel'])
+def fusion(request):
+    """both code paths of the operators that have a single-launch cluster variant (sfb_set_fusion)"""
+    from sparsefusion_b200 import _lib as lib
+    lib.call('sfb_set_fusion', request.param)
+    yield request.param
+    lib.call('sfb_set_fusion', 0x7fffffff)
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
+                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8)])
 @pytest.mark.parametrize('film', [False, True])
-def test_groupnorm_film_silu(shape, film):
+def test_groupnorm_film_silu(shape, film, fusion):
     from sparsefusion_b200 import ops
     nb, h, w, c, g = shape
     x = torch.randn(nb, h, w, c, device='cuda') * 3 + 0.7
@@ -128,11 +138,12 @@ def test_cross_attention():
     _close(out, ref, TF32, 2e-5)
 
 
-def test_gca_pool_and_gate_residual():
+@pytest.mark.parametrize('shape', [(2, 16, 16, 256), (1, 32, 32, 256), (1, 4, 4, 1024), (3, 8, 8, 1024), (2, 3, 1, 64), (1, 16, 16, 512), (1, 8, 8, 96)])
+def test_gca_pool_and_gate_residual(shape, fusion):
     from sparsefusion_b200 import ops
-    nb, h, w, c = 2, 16, 16, 256
-    x = torch.randn(nb, h, w, c, device='cuda')
-    wk, bk = torch.randn(1, c, 1, 1, device='cuda') / 16, torch.randn(1, device='cuda')
+    nb, h, w, c = shape
+    x = torch.randn(nb, h, w, c, device='cuda') * 2
+    wk, bk = torch.randn(1, c, 1, 1, device='cuda') / 8, torch.randn(1, device='cuda')
     pooled = ops.gca_pool(x, wk, bk)
     xd = x.double().view(nb, h * w, c)
     logits = xd @ wk.double().view(c) + bk.double()

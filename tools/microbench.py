@@ -45,9 +45,11 @@ def conv_cases():
 
 def unet_bench(out):
     import numpy as np
-    if 'nocarve' in sys.argv:
-        from sparsefusion_b200 import _lib
-        _lib.call('sfb_set_carveout', 0)
+    from sparsefusion_b200 import _lib
+    if 'nopdl' in sys.argv:
+        _lib.call('sfb_set_pdl', 0)
+    if 'nofuse' in sys.argv:
+        _lib.call('sfb_set_fusion', 0)
     from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
     unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
