@@ -45,8 +45,15 @@ int sfb_get_precision(void);
 /* programmatic dependent launch of the UNet kernels (default on): each kernel may be scheduled while its predecessor drains and
  * waits (griddepcontrol.wait) before touching global memory.  0 restores plain stream-ordered launches (A/B measurement). */
 int sfb_set_pdl(int on);
-/* single-launch fused variants (default all on): bit 0 = cluster GroupNorm (stats + apply in one kernel), bit 1 = cluster global-context
- * pooling (logits + softmax + pooling in one kernel).  Cleared bits select the multi-kernel paths; results agree to fp32 rounding. */
+/* in-situ tracer for the UNet kernels: while a trace is open every traced kernel appends %globaltimer (ns) to device_buf right after its
+ * griddepcontrol.wait (device_buf[0] = number of stamps, device_buf[1..capacity] = stamps; zero it before each run) and the host records
+ * the kernel names in launch order (sfb_trace_names: newline separated, returns the full length).  sfb_trace_end() unbinds.
+ * sfb_trace_end keeps the recorded names readable until the next sfb_trace_begin. */
+int sfb_trace_begin(unsigned long long* device_buf, unsigned int capacity);
+int sfb_trace_end(void);
+int sfb_trace_names(char* out, int capacity);
+/* optional code paths (default all on): bit 0 = the NGP MLP weight gradients run as 3xTF32 tcgen05 GEMMs over the feature-major tapes
+ * (cleared: the fp32 SIMT outer-product kernel).  Both agree to fp32 rounding; the switch exists for A/B measurement and tests. */
 int sfb_set_fusion(int mask);
 /* number of kernels this library has launched so far in this process (bench.py's "gpu_launches") */
 uint64_t sfb_launch_count(void);

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <unordered_set>
 #include "../../include/sparsefusion_b200.h"
@@ -34,12 +35,23 @@ int check_launch(const char* what) {
 }
 
 static int g_precision = 1;  // 0: single-pass TF32 (operands rounded on write); 1: error-compensated 3xTF32 (default)
-int precision_mode() { return g_precision; }
+static thread_local int t_precision_override = -1;
+int precision_mode() { return t_precision_override >= 0 ? t_precision_override : g_precision; }
+int set_precision_override(int m) { const int old = t_precision_override; t_precision_override = m; return old; }
 void set_precision_mode(int m) { g_precision = m; }
 
 static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load() != 0; }
 void set_pdl(int on) { g_pdl.store(on != 0); }
+static std::mutex g_trace_mu;
+static bool g_trace_open = false;
+static std::string g_trace_names;
+void trace_name(const char* kernel) {
+    if (!g_trace_open) return;
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    g_trace_names += kernel;
+    g_trace_names += '\n';
+}
 static std::atomic<int> g_fusion{0x7fffffff};
 int fusion_mask() { return g_fusion.load(); }
 void set_fusion_mask(int m) { g_fusion.store(m); }
@@ -70,6 +82,37 @@ int sfb_set_precision(int mode) {
 }
 int sfb_get_precision(void) { return sfb::precision_mode(); }
 int sfb_set_pdl(int on) { sfb::set_pdl(on); return SFB_OK; }
+int sfb_trace_begin(unsigned long long* device_buf, unsigned int capacity) {
+    {
+        std::lock_guard<std::mutex> lock(sfb::g_trace_mu);
+        sfb::g_trace_names.clear();
+        sfb::g_trace_open = device_buf != nullptr;
+    }
+    sfb::trace_bind_unet_ops(device_buf, capacity);
+    sfb::trace_bind_conv_v2(device_buf, capacity);
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+}
+int sfb_trace_end(void) {
+    {
+        std::lock_guard<std::mutex> lock(sfb::g_trace_mu);
+        sfb::g_trace_open = false;
+    }
+    sfb::trace_bind_unet_ops(nullptr, 0);
+    sfb::trace_bind_conv_v2(nullptr, 0);
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+}
+int sfb_trace_names(char* out, int capacity) {
+    std::lock_guard<std::mutex> lock(sfb::g_trace_mu);
+    const int n = (int)sfb::g_trace_names.size();
+    if (out != nullptr && capacity > 0) {
+        const int m = n < capacity - 1 ? n : capacity - 1;
+        memcpy(out, sfb::g_trace_names.data(), m);
+        out[m] = 0;
+    }
+    return n;
+}
 int sfb_set_fusion(int mask) { sfb::set_fusion_mask(mask); return SFB_OK; }
 uint64_t sfb_launch_count(void) { return (uint64_t)sfb::g_launches.load(); }
 

@@ -24,20 +24,41 @@ void count_launches(int n);            // extra launches made under a single che
 // tensor-core operand precision of the UNet GEMMs: 0 = TF32 single pass, 1 = 3xTF32 (error compensated)
 int precision_mode();
 void set_precision_mode(int m);
+int set_precision_override(int m);   // per host thread; -1 = none.  Returns the previous override (NGP weight gradients always use 3xTF32)
 
 // Programmatic dependent launch (PDL).  The UNet evaluation is ~350 short kernels replayed from one CUDA graph; each of them
 // (a) is launched with programmatic stream serialisation, so its CTAs may become resident while the previous kernel drains, and
 // (b) starts with pdl_sync(): signal that the NEXT kernel may be scheduled, then wait until every kernel before this one has completed
 // and flushed its memory.  All global reads and writes of a kernel come after that wait, so ordering is unchanged.
 bool pdl_enabled();
-// which single-launch fused variants are enabled (sfb_set_fusion): bit 0 GroupNorm cluster kernel, bit 1 global-context pooling cluster kernel
+void trace_name(const char* kernel);   // host side of the tracer: kernel names in launch order while a trace is open
+void trace_bind_unet_ops(unsigned long long* buf, unsigned int cap);
+void trace_bind_conv_v2(unsigned long long* buf, unsigned int cap);
+// optional paths (sfb_set_fusion): bit 0 = NGP MLP weight gradients as tcgen05 GEMMs (off: the SIMT outer-product kernel)
 int fusion_mask();
-static inline bool gn_fused_enabled() { return (fusion_mask() & 1) != 0; }
-static inline bool gca_fused_enabled() { return (fusion_mask() & 2) != 0; }
+static inline bool wgrad_tc_enabled() { return (fusion_mask() & 1) != 0; }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+// In-situ tracer (sfb_trace_begin): when bound, CTA (0,0,0) of every kernel appends %globaltimer to a device buffer right after its
+// griddepcontrol.wait, i.e. at the moment all earlier kernels have completed.  Consecutive stamps are the chain cost of each kernel inside a
+// replayed graph (launch gap included) -- what ncu's serialised, cache-flushed durations cannot show.  buf[0] = count, buf[1..] = stamps.
+static __device__ unsigned long long* t_trace_buf = nullptr;
+static __device__ unsigned int t_trace_cap = 0;
+__device__ __forceinline__ void trace_mark() {
+    unsigned long long* b = t_trace_buf;
+    if (b != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x | threadIdx.y | threadIdx.z) == 0) {
+        const unsigned long long slot = atomicAdd(b, 1ull);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (slot < t_trace_cap) b[1 + slot] = t;
+    }
+}
+static inline void trace_bind_this_tu(unsigned long long* buf, unsigned int cap) {
+    cudaMemcpyToSymbol(t_trace_buf, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(t_trace_cap, &cap, sizeof(cap));
+}
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); trace_mark(); }
 
 // cluster_x > 1 launches thread-block clusters of (cluster_x, 1, 1); grid.x must be a multiple of it
 template <typename... KA, typename... A>
@@ -66,6 +87,8 @@ template <typename... KA, typename... A>
 static inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
     return launch_pdl_cluster(kernel, grid, block, smem, st, 1u, static_cast<A&&>(args)...);
 }
+#define SFB_LAUNCH(kernel, ...) (sfb::trace_name(#kernel), sfb::launch_pdl(kernel, __VA_ARGS__))
+#define SFB_LAUNCH_CLUSTER(kernel, ...) (sfb::trace_name(#kernel), sfb::launch_pdl_cluster(kernel, __VA_ARGS__))
 #endif
 
 

@@ -26,6 +26,7 @@ struct alignas(64) ConvGemmParams {
     int32_t KH, KW, pad, stride;
     int32_t k_iters, splits;
     int32_t accumulate;
+    int32_t raw_hi;         // experiment (variant 3): feed the un-masked fp32 word as the "hi" tensor-core operand (is the hardware's tf32 read a truncation?)
 };
 
 // per-launch CUDA-event timing hooks (bench.py roofline line)

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tf32_kernel(const __gri
     using Cfg = ConvCfg<BN, NP>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET from the __shared__ symbol, so the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     // stage s: [A raw 16 KB | B raw BN*128 B | (NP == 3) A lo | B lo]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + S;
@@ -363,7 +364,7 @@ int sfb_conv_prof_collect(double* total_ms, int* launches, double* weight_bytes,
 }
 
 int sfb_conv_set_variant(int v) {
-    if (v != 1 && v != 2) return fail(SFB_ERR_ARG, "conv_set_variant: 1 or 2");
+    if (v < 1 || v > 3) return fail(SFB_ERR_ARG, "conv_set_variant: 1, 2 or 3 (3 = 2 with un-masked hi operands, experiment)");
     g_variant = v;
     return SFB_OK;
 }
@@ -389,7 +390,7 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
     // are the N side (16 / 32 / 64 of them) and 128 output channels the M side.
     const int planeW = (stride == 2) ? W / 2 : W, planeH = (stride == 2) ? H / 2 : H;
     const int64_t P_total = (int64_t)NB * Ho * Wo;
-    const bool v2 = (precision_mode() == 1 && g_variant == 2);
+    const bool v2 = (precision_mode() == 1 && g_variant >= 2);
     const bool swap = v2 && P_total <= 64 && bn <= 0;
     int tile_pix = kBM;
     if (swap) { tile_pix = 16; while (tile_pix < P_total) tile_pix *= 2; }
@@ -408,6 +409,7 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
     p.k_iters = KH * KW * p.cin_chunks;
     p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.out = out; p.bias = bias; p.ldo = ldo; p.accumulate = accumulate;
+    p.raw_hi = (g_variant == 3) ? 1 : 0;
     p.residual = residual; p.ldr = ldr;
     SFB_REQUIRE(residual == nullptr || (ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0), "conv2d_nhwc_tf32: residual must be 16-byte aligned");
 

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     using Cfg = Conv2Cfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET from the __shared__ symbol, so the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + S;
     uint64_t* conv_bar = empty_bar + S;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 load_weights(it);
             }
             pdl_wait();
+            trace_mark();
             for (int it = 0; it < pre; ++it) load_acts(it);
             for (int it = pre; it < niter; ++it) {
                 const int s = it % S;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-                        hi[c * 4 + e] = h;
+                        hi[c * 4 + e] = p.raw_hi ? __float_as_uint(f[e]) : h;
                         lo[c * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
                     }
                 }
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                     h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
                     h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
                     h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    nraw[i] = h;
+                    if (!p.raw_hi) nraw[i] = h;
                     nlo[i] = l;
                 }
             }
@@ -304,10 +306,14 @@ static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
         configured = true;
     }
     conv_prof_begin(st);
+    trace_name(SWAP ? (BN == 16 ? "conv_v2<16,swap>" : BN == 32 ? "conv_v2<32,swap>" : "conv_v2<64,swap>")
+                    : (BN == 16 ? "conv_v2<16>" : BN == 32 ? "conv_v2<32>" : BN == 64 ? "conv_v2<64>" : BN == 128 ? "conv_v2<128>" : "conv_v2<256>"));
     launch_pdl(conv_gemm_v2_kernel<BN, SWAP>, grid, dim3(kThreads), Conv2Cfg<BN>::kSmemBytes, st, p);
     conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32(v2)");
 }
+
+void trace_bind_conv_v2(unsigned long long* buf, unsigned int cap) { trace_bind_this_tu(buf, cap); }
 
 int launch_conv_v2(const ConvGemmParams& p, int BN, bool swap, dim3 grid, cudaStream_t st) {
     if (swap) {

@@ -312,6 +312,29 @@ __global__ void __launch_bounds__(kFieldThreads) field_backward_kernel(PointSour
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradients
+// db[j] += sum_p D[j][p] for the rows of D1 | D2 | D3 (contiguous [2*kHid + kOut][Bp]); grid (chunks, rows)
+__global__ void __launch_bounds__(256) tape_rowsum_kernel(const float* __restrict__ D, uint32_t Bp, float* __restrict__ gb0, float* __restrict__ gb1,
+                                                         float* __restrict__ gb2) {
+    const int row = blockIdx.y;
+    const float4* r4 = reinterpret_cast<const float4*>(D + (size_t)row * Bp);
+    const uint32_t n4 = Bp >> 2;   // Bp is a multiple of 64
+    float s = 0.f;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n4; i += gridDim.x * 256u) {
+        const float4 v = __ldg(r4 + i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    __shared__ float sh[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        float* dst = row < kHid ? gb0 + row : (row < 2 * kHid ? gb1 + (row - kHid) : gb2 + (row - 2 * kHid));
+        atomicAdd(dst, t);
+    }
+}
+
 // dW[j][k] += sum_p D[j][p] * H[k][p];  db[j] += sum_p D[j][p].   D [J][Bp], H [K][Bp] feature-major.
 // CTA = 256 threads as a 16x16 grid of (J/16 x K/16) register tiles; points staged through smem 64 at a time.
 template <int J, int K>
@@ -442,6 +465,22 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
                                                               FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, grad_sigma, grad_rgb,
                                                               grad_embeddings, H0, H1, H2, D1, D2, D3);
     if (int rc = check_launch("ngp_field_backward(data)")) return rc;
+    if (wgrad_tc_enabled()) {
+        // dW = D . H^T with the point index as the GEMM's K dimension: the feature-major tapes are exactly the K-major operands the tcgen05
+        // implicit-GEMM kernel streams (rows of D = "pixels", rows of H = "output channels", 1x1 tap), 3xTF32, split-K over the 2.1 M points
+        // with fp32 reductions into the gradient buffers (accumulate = 1).  Bias gradients are row sums of D.
+        const int old = set_precision_override(1);
+        int rc = sfb_conv2d_nhwc_tf32(D1, 1, 1, kHid, (int)Bp, (int64_t)Bp, H0, kIn, 1, 1, 1, 0, nullptr, nullptr, 0, gW0, kIn, 1, 0, 0, stream);
+        if (!rc) rc = sfb_conv2d_nhwc_tf32(D2, 1, 1, kHid, (int)Bp, (int64_t)Bp, H1, kHid, 1, 1, 1, 0, nullptr, nullptr, 0, gW1, kHid, 1, 0, 0, stream);
+        if (!rc) rc = sfb_conv2d_nhwc_tf32(D3, 1, 1, kOut, (int)Bp, (int64_t)Bp, H2, kHid, 1, 1, 1, 0, nullptr, nullptr, 0, gW2, kHid, 1, 0, 0, stream);
+        set_precision_override(old);
+        if (rc) return rc;
+        // D1, D2, D3 are contiguous in the tape: one launch sums all 2*kHid + kOut rows
+        const int rows = 2 * kHid + kOut;
+        const uint32_t chunks = min(ceil_div(Bp, 4096u), 64u);
+        tape_rowsum_kernel<<<dim3(chunks, rows), 256, 0, st>>>(D1, Bp, gb0, gb1, gb2);
+        return check_launch("ngp_field_backward(bias)");
+    }
     const uint32_t wb = min(Bp / 64, (uint32_t)sm_count() * 2);
     mlp_wgrad_kernel<kHid, kIn><<<wb, 256, 0, st>>>(D1, H0, Bp, gW0, gb0);
     mlp_wgrad_kernel<kHid, kHid><<<wb, 256, 0, st>>>(D2, H1, Bp, gW1, gb1);

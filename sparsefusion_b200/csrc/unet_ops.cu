@@ -9,7 +9,6 @@
 // streaming GEMVs and stay in full fp32.
 // Tensors that feed a tcgen05 GEMM are rounded to TF32 (cvt.rna) when they are written here, so the
 // tensor core's operand truncation never biases the result.
-#include <cooperative_groups.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include "../../include/sparsefusion_b200.h"
@@ -111,11 +110,11 @@ __global__ void pixel_shuffle_silu_kernel(const float* __restrict__ y, float* __
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
-// CTAs (group, n, pixel-slab): partial fp64 (sum, sumsq) per slab; the last slab to finish folds the partials into (mean, rstd).
-// `counters` is a persistent zero-initialised buffer (one uint per (n, group)); the finishing CTA resets its counter.
-__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps, int S,
-                                                      double2* __restrict__ partial, unsigned int* __restrict__ counters,
-                                                      float2* __restrict__ stats) {
+// Two launches, no atomics: (1) CTAs (group, n, pixel-slab) write fp64 partial (sum, sumsq) per slab; (2) every CTA of the apply kernel
+// folds the <= 64 partials of its image's groups into (mean, rstd) in shared memory (one warp per group) and normalises its pixels.
+// (The earlier "last CTA finalises" variant cost 5.5-6.6 us per launch in the replayed graph: threadfence + counter atomics.)
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, int S,
+                                                      double2* __restrict__ partial) {
     pdl_sync();
     const int g = blockIdx.x, n = blockIdx.y, sl = blockIdx.z;
     const int Cg = C / G;
@@ -134,7 +133,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         ss += (double)b;
     }
     __shared__ double sh_s[8], sh_ss[8];
-    __shared__ bool is_last;
     s = warp_sum_d(s);
     ss = warp_sum_d(ss);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,40 +142,47 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         const int nw = blockDim.x >> 5;
         s = 0.0; ss = 0.0;
         for (int w = 0; w < nw; ++w) { s += sh_s[w]; ss += sh_ss[w]; }
-        const int slot = n * G + g;
-        partial[(int64_t)slot * S + sl] = make_double2(s, ss);
-        __threadfence();
-        const unsigned int done = atomicAdd(&counters[slot], 1u);
-        is_last = (done == (unsigned int)(S - 1));
-        if (is_last) {
-            __threadfence();
-            double ts = 0.0, tss = 0.0;
-            for (int k = 0; k < S; ++k) {
-                const volatile double* pr = reinterpret_cast<volatile double*>(&partial[(int64_t)slot * S + k]);
-                ts += pr[0]; tss += pr[1];
-            }
+        partial[((int64_t)n * G + g) * S + sl] = make_double2(s, ss);
+    }
+}
+
+// y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ), rounded to tf32.  film [NB, 2C] (scale | shift) or null.  grid (blocks, NB)
+constexpr int kGnMaxGroups = 32;
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const double2* __restrict__ partial, int S, float eps,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
+                                                      int G, int act, int round) {
+    pdl_sync();
+    __shared__ float2 st_sh[kGnMaxGroups];
+    const int n = blockIdx.y;
+    const int Cg = C / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < G; g += 8) {
+        double ts = 0.0, tss = 0.0;
+        for (int k = lane; k < S; k += 32) {
+            const double2 pr = partial[((int64_t)n * G + g) * S + k];
+            ts += pr.x; tss += pr.y;
+        }
+        ts = warp_sum_d(ts);
+        tss = warp_sum_d(tss);
+        if (lane == 0) {
             const double cnt = (double)HW * Cg;
             const double mean = ts / cnt;
             double var = tss / cnt - mean * mean;
             if (var < 0) var = 0;
-            stats[slot] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-            counters[slot] = 0u;
+            st_sh[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
         }
     }
-}
-
-// y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ), rounded to tf32.  film [NB, 2C] (scale | shift) or null
-__global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
-                                int G, int act, int round, int64_t total4) {
-    pdl_sync();
-    const int C4 = C >> 2, Cg = C / G;
+    __syncthreads();
+    const int C4 = C >> 2;
+    const int64_t total4 = (int64_t)HW * C4;
+    const float* xn = x + (int64_t)n * HW * ldx;
+    float* yn = y + (int64_t)n * HW * ldy;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = i / C4;
         const int c = (int)(i - pix * C4) * 4;
-        const int n = (int)(pix / HW);
-        const float2 st = __ldg(stats + n * G + c / Cg);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + pix * ldx + c));
+        const float2 st = st_sh[c / Cg];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xn + pix * ldx + c));
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
         float o[4] = {(v.x - st.x) * st.y * ga.x + be.x, (v.y - st.x) * st.y * ga.y + be.y, (v.z - st.x) * st.y * ga.z + be.z,
@@ -196,93 +201,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const 
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = tc::round_tf32(o[k]);
         }
-        *reinterpret_cast<float4*>(y + pix * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// Single-launch GroupNorm for the sizes of a B<=8 UNet evaluation: one thread-block CLUSTER per (n, group), CTA r of the cluster owns a
-// slab of pixels, keeps its <= 8 float4 per thread in registers, publishes fp64 (sum, sumsq) in shared memory, reads the other CTAs'
-// partials through distributed shared memory and applies affine / FiLM / SiLU straight from the registers -- x is read once.
-constexpr int kGnFusedItems = 8;   // float4 per thread
-__global__ void __launch_bounds__(256) gn_fused_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int act,
-                                                       int round) {
-    pdl_sync();
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int R = (int)gridDim.x, sl = (int)blockIdx.x, g = blockIdx.y, n = blockIdx.z;
-    const int Cg = C / G, Cg4 = Cg >> 2;
-    const int p0 = (int)(((int64_t)HW * sl) / R), p1 = (int)(((int64_t)HW * (sl + 1)) / R);
-    const int total4 = (p1 - p0) * Cg4;
-    const float* base = x + ((int64_t)n * HW + p0) * ldx + g * Cg;
-    float4 v[kGnFusedItems];
-    double s = 0.0, ss = 0.0;
-#pragma unroll
-    for (int k = 0; k < kGnFusedItems; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < total4) {
-            const int pix = i / Cg4, c4 = i - pix * Cg4;
-            v[k] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * ldx) + c4);
-            s += (double)(v[k].x + v[k].y + v[k].z + v[k].w);
-            ss += (double)(v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w);
-        }
-    }
-    __shared__ double sh_s[8], sh_ss[8];
-    __shared__ double part[2];
-    __shared__ float2 st_sh;
-    s = warp_sum_d(s);
-    ss = warp_sum_d(ss);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; ++w) { a += sh_s[w]; b += sh_ss[w]; }
-        part[0] = a; part[1] = b;
-    }
-    cluster.sync();
-    if (threadIdx.x == 0) {
-        double ts = 0.0, tss = 0.0;
-        for (int r = 0; r < R; ++r) {
-            const double* rp = cluster.map_shared_rank(part, r);
-            ts += rp[0]; tss += rp[1];
-        }
-        const double cnt = (double)HW * Cg;
-        const double mean = ts / cnt;
-        double var = tss / cnt - mean * mean;
-        if (var < 0) var = 0;
-        st_sh = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-    }
-    cluster.sync();   // also keeps every CTA's `part` alive until all remote reads are done
-    const float2 st = st_sh;
-    float* ybase = y + ((int64_t)n * HW + p0) * ldy + g * Cg;
-#pragma unroll
-    for (int k = 0; k < kGnFusedItems; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < total4) {
-            const int pix = i / Cg4, c4 = i - pix * Cg4;
-            const int c = g * Cg + c4 * 4;
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-            float o[4] = {(v[k].x - st.x) * st.y * ga.x + be.x, (v[k].y - st.x) * st.y * ga.y + be.y, (v[k].z - st.x) * st.y * ga.z + be.z,
-                          (v[k].w - st.x) * st.y * ga.w + be.w};
-            if (film) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + c));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + C + c));
-                o[0] = o[0] * (sc.x + 1.f) + sh.x; o[1] = o[1] * (sc.y + 1.f) + sh.y;
-                o[2] = o[2] * (sc.z + 1.f) + sh.z; o[3] = o[3] * (sc.w + 1.f) + sh.w;
-            }
-            if (act) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
-            }
-            if (round) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = tc::round_tf32(o[e]);
-            }
-            *(reinterpret_cast<float4*>(ybase + (int64_t)pix * ldy) + c4) = make_float4(o[0], o[1], o[2], o[3]);
-        }
+        *reinterpret_cast<float4*>(yn + pix * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -445,6 +364,73 @@ __global__ void mq_attention_kernel(const float* __restrict__ q, const float* __
     }
 }
 
+// Same contract, keys/values staged in shared memory.  All heads share one K/V (multi-query), so a CTA of 8 warps (8 queries of one image) loads
+// the nk x 2 x dh block once, coalesced; the per-key dot products and the P.V sums then run at shared-memory latency.  (The global-memory
+// kernel above walks the keys with one dependent L2 round trip per key: 28 us for 19 keys in the replayed graph.)
+__global__ void __launch_bounds__(256) mq_attention_smem_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                const float* __restrict__ null_kv, const float* __restrict__ ckv,
+                                                                float* __restrict__ out, int n, int heads, int dh, int nc, float scale, int round) {
+    pdl_sync();
+    extern __shared__ float sm[];
+    const int nk = nc + 1 + n;
+    const int row = 2 * dh;                 // k | v of one key
+    float* kvs = sm;                        // [nk][2*dh]
+    float* scs = sm + (size_t)nk * row;     // [8][nk]
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // stage: context keys, the null key, the image's tokens (imagen_pytorch.py:523-532 key order)
+    const int row4 = row >> 2;
+    for (int i = threadIdx.x; i < nk * row4; i += 256) {
+        const int j = i / row4, e4 = i - j * row4;
+        const float* src;
+        if (j < nc) src = ckv + ((int64_t)(b * nc + j)) * row;
+        else if (j == nc) src = null_kv;
+        else src = kv + ((int64_t)(b * n + (j - nc - 1))) * row;
+        reinterpret_cast<float4*>(kvs)[i] = __ldg(reinterpret_cast<const float4*>(src) + e4);
+    }
+    __syncthreads();
+    const int qi = blockIdx.x * 8 + warp;   // query index over (head, token)
+    if (qi >= heads * n) return;
+    const int i = qi % n, h = qi / n;
+    const float* qr = q + ((int64_t)(b * n + i) * heads + h) * dh;
+    float qv[4];                            // dh <= 128
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qv[t] = (lane + 32 * t < dh) ? qr[lane + 32 * t] * scale : 0.f;
+    float* sc = scs + warp * nk;
+    float mx = -INFINITY;
+    for (int j = 0; j < nk; ++j) {
+        const float* kr = kvs + (size_t)j * row;
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (lane + 32 * t < dh) d += qv[t] * kr[lane + 32 * t];
+        d = warp_sum(d);
+        if (lane == 0) sc[j] = d;
+        mx = fmaxf(mx, d);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < nk; j += 32) { const float e = __expf(sc[j] - mx); sc[j] = e; den += e; }
+    den = warp_sum(den);
+    __syncwarp();
+    const float inv = 1.f / den;
+    float* orow = out + ((int64_t)(b * n + i) * heads + h) * dh;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < nk; ++j) {
+        const float pj = sc[j];
+        const float* vr = kvs + (size_t)j * row + dh;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (lane + 32 * t < dh) acc[t] += pj * vr[lane + 32 * t];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < dh) {
+            const float v = acc[t] * inv;
+            orow[lane + 32 * t] = round ? tc::round_tf32(v) : v;
+        }
+}
+
 // Cross attention (imagen_pytorch.py:764-805): q [B,n,heads*dh]; kvc [B,nc,2*heads*dh] = (k | v) per context token, per-head slices;
 // null_kv [2,dh] shared by heads; keys: null, context.  One warp per (b, head, query).
 __global__ void cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const float* __restrict__ null_kv,
@@ -498,90 +484,22 @@ __global__ void gca_logits_kernel(const float* __restrict__ x, int64_t ldx, cons
     d = warp_sum(d);
     if (lane == 0) logits[p] = d + bk[0];
 }
-// softmax statistics of one image's logits -> stat[n] = (max, 1/sum exp); also zeroes pooled[n][:] for the accumulation pass
-__global__ void __launch_bounds__(256) gca_stats_kernel(const float* __restrict__ logits, float2* __restrict__ stat, float* __restrict__ pooled,
-                                                       int HW, int C) {
+// pooled[n][c] = sum_p softmax(logits[n])[p] * x[n][p][c].  grid (C / 16, NB): a CTA owns 16 channels of one image -- no atomics, no
+// zero-init.  Each CTA first turns the image's logits into softmax weights in shared memory (HW floats; redundant across CTAs, trivial),
+// then thread (pixel group pg of 64, float4 column q of 4) accumulates pixels pg, pg + 64, ...; the 64 partial rows fold through smem.
+constexpr int kGcaCols = 16;
+__global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
+                                                      float* __restrict__ pooled, int HW, int C) {
     pdl_sync();
+    extern __shared__ float gca_sm[];
+    float* wts = gca_sm;                       // [HW]
+    float* part = gca_sm + ((HW + 3) & ~3);    // [64][16]
     __shared__ float red[8];
-    const int n = blockIdx.x;
+    const int n = blockIdx.y, c0 = blockIdx.x * kGcaCols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* lg = logits + (int64_t)n * HW;
     float mx = -INFINITY;
-    for (int p = threadIdx.x; p < HW; p += 256) mx = fmaxf(mx, lg[p]);
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-    __syncthreads();
-    float sm = 0.f;
-    for (int p = threadIdx.x; p < HW; p += 256) sm += __expf(lg[p] - mx);
-    sm = warp_sum(sm);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sm;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        stat[n] = make_float2(mx, 1.f / t);
-    }
-    for (int c = threadIdx.x; c < C; c += 256) pooled[(int64_t)n * C + c] = 0.f;
-}
-// pooled[n][c] += sum_{p in slab} softmax(logits)[p] * x[n][p][c]      grid (slabs of 16 pixels, NB), threads = channels
-__global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
-                                                      const float2* __restrict__ stat, float* __restrict__ pooled, int HW, int C) {
-    pdl_sync();
-    constexpr int SLAB = 16;
-    __shared__ float wts[SLAB];
-    const int n = blockIdx.y, p0 = blockIdx.x * SLAB;
-    const int np = min(SLAB, HW - p0);
-    const float2 st = stat[n];
-    if (threadIdx.x < np) wts[threadIdx.x] = __expf(logits[(int64_t)n * HW + p0 + threadIdx.x] - st.x) * st.y;
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const float* xb = x + ((int64_t)n * HW + p0) * ldx + c;
-        float acc = 0.f;
-#pragma unroll 4
-        for (int p = 0; p < np; ++p) acc += wts[p] * __ldg(xb + (int64_t)p * ldx);
-        atomicAdd(pooled + (int64_t)n * C + c, acc);
-    }
-}
-
-// Single-launch GlobalContext pooling: one cluster of R CTAs per image, CTA r owns a slab of pixels.  Per CTA: logits of its pixels (warp per
-// pixel), slab-local softmax statistics (m_r, l_r) and the slab-local weighted channel sums P_r[c] = sum_p exp(logit_p - m_r) x[p][c]; after a
-// cluster barrier CTA r combines channel slice r of all slabs through distributed shared memory:
-//   pooled[c] = sum_r e^{m_r - m} P_r[c] / sum_r e^{m_r - m} l_r,   m = max_r m_r            (the flash-attention merge; C <= 1024, slab <= 256 px)
-constexpr int kGcaMaxC = 1024, kGcaMaxSlab = 256;
-__global__ void __launch_bounds__(256) gca_fused_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ wk,
-                                                       const float* __restrict__ bk, float* __restrict__ pooled, int HW, int C) {
-    pdl_sync();
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ float wts[kGcaMaxSlab];
-    __shared__ __align__(16) float part[1024];
-    __shared__ __align__(16) float pp[kGcaMaxC];
-    __shared__ float red[8];
-    __shared__ float ml[2];
-    const int R = (int)gridDim.x, sl = (int)blockIdx.x, n = blockIdx.y;
-    const int p0 = (int)(((int64_t)HW * sl) / R), p1 = (int)(((int64_t)HW * (sl + 1)) / R);
-    const int np = p1 - p0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* xb = x + ((int64_t)n * HW + p0) * ldx;
-    const float b0 = __ldg(bk);
-    // (1) logits
-    for (int p = warp; p < np; p += 8) {
-        const float* xr = xb + (int64_t)p * ldx;
-        float d = 0.f;
-        for (int c = lane * 4; c < C; c += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wk + c));
-            d += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
-        }
-        d = warp_sum(d);
-        if (lane == 0) wts[p] = d + b0;
-    }
-    __syncthreads();
-    // (2) slab-local max and exp-sum; wts <- exp(logit - m_r)
-    float mx = -INFINITY;
-    for (int p = threadIdx.x; p < np; p += 256) mx = fmaxf(mx, wts[p]);
+    for (int p = threadIdx.x; p < HW; p += 256) { const float v = lg[p]; wts[p] = v; mx = fmaxf(mx, v); }
     mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
     __syncthreads();
@@ -590,55 +508,34 @@ __global__ void __launch_bounds__(256) gca_fused_kernel(const float* __restrict_
     for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
     __syncthreads();
     float sm = 0.f;
-    for (int p = threadIdx.x; p < np; p += 256) {
-        const float e = __expf(wts[p] - mx);
-        wts[p] = e;
-        sm += e;
-    }
+    for (int p = threadIdx.x; p < HW; p += 256) { const float e = __expf(wts[p] - mx); wts[p] = e; sm += e; }
     sm = warp_sum(sm);
     if (lane == 0) red[warp] = sm;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        ml[0] = mx; ml[1] = t;
-    }
-    // (3) P_r[c]: thread = (pixel group, float4 column); groups split the slab's pixels, then fold through shared memory
-    const int ncol = C >> 2;                       // <= 256
-    const int ngrp = 256 / ncol;                   // >= 1
-    const int grp = threadIdx.x / ncol, col = threadIdx.x - grp * ncol;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float inv = 1.f / tot;
+    const int pg = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const int c = c0 + q * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (grp < ngrp) {
+    if (c < C) {
+        const float* xb = x + (int64_t)n * HW * ldx + c;
 #pragma unroll 4
-        for (int p = grp; p < np; p += ngrp) {
+        for (int p = pg; p < HW; p += 64) {
             const float w = wts[p];
-            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)p * ldx) + col);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)p * ldx));
             acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
         }
-        reinterpret_cast<float4*>(part)[grp * ncol + col] = acc;
     }
+    reinterpret_cast<float4*>(part)[pg * 4 + q] = acc;
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
+    if (threadIdx.x < kGcaCols && c0 + threadIdx.x < C) {
         float t = 0.f;
-        for (int g = 0; g < ngrp; ++g) t += part[g * C + c];
-        pp[c] = t;
+#pragma unroll 8
+        for (int g = 0; g < 64; ++g) t += part[g * kGcaCols + threadIdx.x];
+        pooled[(int64_t)n * C + c0 + threadIdx.x] = t * inv;
     }
-    cluster.sync();
-    // (4) merge channel slice `sl` across the cluster's slabs
-    float m = -INFINITY;
-    for (int r = 0; r < R; ++r) m = fmaxf(m, cluster.map_shared_rank(ml, r)[0]);
-    float den = 0.f;
-    for (int r = 0; r < R; ++r) {
-        const float* rml = cluster.map_shared_rank(ml, r);
-        den += __expf(rml[0] - m) * rml[1];
-    }
-    const int c0 = (int)(((int64_t)C * sl) / R), c1 = (int)(((int64_t)C * (sl + 1)) / R);
-    for (int c = c0 + threadIdx.x; c < c1; c += 256) {
-        float t = 0.f;
-        for (int r = 0; r < R; ++r) t += __expf(cluster.map_shared_rank(ml, r)[0] - m) * cluster.map_shared_rank(pp, r)[c];
-        pooled[(int64_t)n * C + c] = t / den;
-    }
-    cluster.sync();   // keep this CTA's shared memory alive until every remote read is done
 }
 
 // out = h * gate[n][c] + res      (ResnetBlock tail, imagen_pytorch.py:727-729); gate may be null (== 1)
@@ -659,6 +556,8 @@ __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v
     }
 }
 
+void trace_bind_unet_ops(unsigned long long* buf, unsigned int cap) { trace_bind_this_tu(buf, cap); }
+
 static inline int ew_blocks(int64_t total, int threads = 256) {
     int64_t b = (total + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -674,14 +573,14 @@ extern "C" {
 int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream) {
     SFB_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    launch_pdl(nchw_to_nhwc_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
+    SFB_LAUNCH(nchw_to_nhwc_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld, c_off, round_tf32 && precision_mode() == 0);
     return check_launch("nchw_to_nhwc");
 }
 
 int sfb_nhwc_to_nchw(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, void* stream) {
     SFB_REQUIRE(src && dst, "nhwc_to_nchw: null pointer");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), NB), block(32, 8);
-    launch_pdl(nhwc_to_nchw_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld);
+    SFB_LAUNCH(nhwc_to_nchw_kernel, grid, block, 0, as_stream(stream), src, dst, C, H * W, ld);
     return check_launch("nhwc_to_nchw");
 }
 
@@ -690,7 +589,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
     SFB_REQUIRE(a && b && out, "concat2_nhwc: null pointer");
     SFB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0, "concat2_nhwc: channel counts must be multiples of 4");
     const int64_t total = npix * ((C1 + C2) / 4);
-    launch_pdl(concat2_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
+    SFB_LAUNCH(concat2_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(a), C1 / 4, lda / 4,
                                                                     reinterpret_cast<const float4*>(b), C2 / 4, ldb / 4, scale_b,
                                                                     reinterpret_cast<float4*>(out), ldo / 4, npix);
     return check_launch("concat2_nhwc");
@@ -699,7 +598,7 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream) {
     SFB_REQUIRE(y && out, "pixel_shuffle_silu: null pointer");
     const int64_t total = (int64_t)NB * 4 * H * W * Co;
-    launch_pdl(pixel_shuffle_silu_kernel, ew_blocks(total), 256, 0, as_stream(stream), y, out, H, W, Co, ldo, total);
+    SFB_LAUNCH(pixel_shuffle_silu_kernel, ew_blocks(total), 256, 0, as_stream(stream), y, out, H, W, Co, ldo, total);
     return check_launch("pixel_shuffle_silu");
 }
 
@@ -711,35 +610,28 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     SFB_REQUIRE(((uintptr_t)stats_ws & 15) == 0, "groupnorm_nhwc: workspace must be 16-byte aligned");
     SFB_REQUIRE(C % G == 0 && (C / G) % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "groupnorm_nhwc: channels per group must be a multiple of 4");
     cudaStream_t st = as_stream(stream);
-    {   // single-launch cluster path: the (n, group) slab split over R <= 8 CTAs must fit 8 float4 per thread
-        const int64_t group4 = (int64_t)HW * (C / G / 4);
-        int R = 1;
-        while (R < 8 && (group4 + R - 1) / R > 256 * kGnFusedItems) R *= 2;
-        const bool fits = (((int64_t)HW + R - 1) / R) * (C / G / 4) <= 256 * kGnFusedItems && HW >= R && NB <= 65535;
-        if (fits && gn_fused_enabled()) {
-            launch_pdl_cluster(gn_fused_kernel, dim3(R, G, NB), dim3(256), 0, st, (unsigned)R, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy,
-                               act_silu, (int)(precision_mode() == 0));
-            return check_launch("groupnorm_nhwc(fused)");
-        }
-    }
-    // workspace: [0, 2*NB*G) floats = (mean, rstd); then 16-byte aligned fp64 partials [NB*G*S][2]
+    // workspace: 16-byte aligned fp64 partials [NB*G*S][2] (the leading (mean, rstd) slots of the old layout stay unused)
+    SFB_REQUIRE(G <= kGnMaxGroups, "groupnorm_nhwc: at most 32 groups");
     int S = 1;
     while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
-    float2* stats = reinterpret_cast<float2*>(stats_ws);
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
-    SFB_REQUIRE(counters != nullptr, "groupnorm_nhwc: counters workspace is null");
-    launch_pdl(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, eps, S, partial, counters, stats);
+    (void)counters;
+    SFB_LAUNCH(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, S, partial);
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
-    const int64_t total4 = (int64_t)NB * HW * (C / 4);
-    launch_pdl(gn_apply_kernel, ew_blocks(total4), 256, 0, st, x, ldx, reinterpret_cast<const float2*>(stats_ws), gamma, beta, film, film_ld, y, ldy, HW, C, G,
-                                                      act_silu, precision_mode() == 0, total4);
+    const int64_t img4 = (int64_t)HW * (C / 4);
+    int ab = (int)((img4 + 256 * 4 - 1) / (256 * 4));     // ~4 float4 per thread
+    const int cap = (sm_count() * 8) / (NB < 1 ? 1 : NB);
+    if (ab > cap) ab = cap < 1 ? 1 : cap;
+    if (ab < 1) ab = 1;
+    SFB_LAUNCH(gn_apply_kernel, dim3(ab, NB), 256, 0, st, x, ldx, (const double2*)partial, S, eps, gamma, beta, film, film_ld, y, ldy, HW, C, G, act_silu,
+               (int)(precision_mode() == 0));
     return check_launch("groupnorm_nhwc(apply)");
 }
 
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,
                        int C, int pre_gelu, int round_tf32, void* stream) {
     SFB_REQUIRE(x && g && y, "layernorm_rows: null pointer");
-    launch_pdl(layernorm_rows_kernel, T, 128, 0, as_stream(stream), x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
+    SFB_LAUNCH(layernorm_rows_kernel, T, 128, 0, as_stream(stream), x, ldx, g, b, res, ldr, y, ldy, T, C, pre_gelu, round_tf32 && precision_mode() == 0);
     return check_launch("layernorm_rows");
 }
 
@@ -752,13 +644,13 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
         const size_t sm = (size_t)2 * K * 4;
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)); cfg = true; }
-        launch_pdl(linear_small_kernel<2>, dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        SFB_LAUNCH(linear_small_kernel<2>, dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     } else {
         const size_t sm = (size_t)8 * K * 4;
         SFB_REQUIRE(sm <= 200 * 1024, "linear_small: K too large for 8-row tile");
         static bool cfg = false;
         if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-        launch_pdl(linear_small_kernel<8>, dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
+        SFB_LAUNCH(linear_small_kernel<8>, dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     }
     return check_launch("linear_small");
 }
@@ -766,7 +658,7 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
 int sfb_time_fourier(const float* t, const float* w, float* out, int B, int half, void* stream) {
     SFB_REQUIRE(t && w && out, "time_fourier: null pointer");
     const int total = B * (2 * half + 1);
-    launch_pdl(time_fourier_kernel, ceil_div(total, 128), 128, 0, as_stream(stream), t, w, out, B, half);
+    SFB_LAUNCH(time_fourier_kernel, ceil_div(total, 128), 128, 0, as_stream(stream), t, w, out, B, half);
     return check_launch("time_fourier");
 }
 
@@ -774,10 +666,20 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
                      float scale, void* stream) {
     SFB_REQUIRE(q && kv && null_kv && out && (nc == 0 || ckv), "mq_attention: null pointer");
     const int nk = nc + 1 + n;
+    {
+        const size_t sm2 = ((size_t)nk * 2 * dh + (size_t)8 * nk) * 4;
+        if (dh % 4 == 0 && dh <= 128 && sm2 <= 160 * 1024) {
+            static bool cfg = false;
+            if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(mq_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg = true; }
+            SFB_LAUNCH(mq_attention_smem_kernel, dim3(ceil_div(heads * n, 8), B), 256, sm2, as_stream(stream), q, kv, null_kv, ckv, out, n, heads, dh, nc, scale,
+                       (int)(precision_mode() == 0));
+            return check_launch("mq_attention");
+        }
+    }
     const int warps = 4;
     const size_t sm = (size_t)warps * nk * 4;
     SFB_REQUIRE(sm <= 48 * 1024, "mq_attention: too many keys for the single-pass kernel");
-    launch_pdl(mq_attention_kernel, ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream), q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    SFB_LAUNCH(mq_attention_kernel, ceil_div(B * heads * n, warps), warps * 32, sm, as_stream(stream), q, kv, null_kv, ckv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("mq_attention");
 }
 
@@ -785,7 +687,7 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
                         void* stream) {
     SFB_REQUIRE(q && kvc && null_kv && out, "cross_attention: null pointer");
     SFB_REQUIRE(nc <= 8, "cross_attention: at most 8 context tokens");
-    launch_pdl(cross_attention_kernel, ceil_div(B * heads * n, 4), 128, 0, as_stream(stream), q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
+    SFB_LAUNCH(cross_attention_kernel, ceil_div(B * heads * n, 4), 128, 0, as_stream(stream), q, kvc, null_kv, out, B, n, heads, dh, nc, scale, precision_mode() == 0);
     return check_launch("cross_attention");
 }
 
@@ -795,19 +697,11 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0, "gca_pool: unsupported shape");
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)NB * HW;
-    if (gca_fused_enabled() && C <= kGcaMaxC && 1024 % C == 0 && HW <= 8 * kGcaMaxSlab && NB <= 65535) {
-        int R = 8;
-        while (R > 1 && R > HW) R >>= 1;
-        launch_pdl_cluster(gca_fused_kernel, dim3(R, NB), dim3(256), 0, st, (unsigned)R, x, ldx, wk, bk, pooled, HW, C);
-        return check_launch("gca_pool(fused)");
-    }
-    launch_pdl(gca_logits_kernel, (unsigned)ceil_div(npix, (int64_t)8), 256, 0, st, x, ldx, wk, bk, logits_ws, npix, C);
+    SFB_LAUNCH(gca_logits_kernel, (unsigned)ceil_div(npix, (int64_t)8), 256, 0, st, x, ldx, wk, bk, logits_ws, npix, C);
     if (int rc = check_launch("gca_pool(logits)")) return rc;
-    // logits_ws: NB*HW logits followed by NB (max, 1/sum) pairs
-    float2* stat = reinterpret_cast<float2*>(logits_ws + ((npix + 1) / 2) * 2);
-    launch_pdl(gca_stats_kernel, NB, 256, 0, st, logits_ws, stat, pooled, HW, C);
-    if (int rc = check_launch("gca_pool(stats)")) return rc;
-    launch_pdl(gca_pool_kernel, dim3(ceil_div(HW, 16), NB), 256, 0, st, x, ldx, logits_ws, stat, pooled, HW, C);
+    const size_t sm = ((size_t)((HW + 3) & ~3) + 64 * kGcaCols) * 4;
+    SFB_REQUIRE(sm <= 48 * 1024, "gca_pool: image too large for the single-pass pooling kernel");
+    SFB_LAUNCH(gca_pool_kernel, dim3(ceil_div(C, kGcaCols), NB), 256, sm, st, x, ldx, logits_ws, pooled, HW, C);
     return check_launch("gca_pool(pool)");
 }
 
@@ -816,7 +710,7 @@ int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const
     SFB_REQUIRE(h && res && out, "gate_residual: null pointer");
     SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0, "gate_residual: channel counts must be multiples of 4");
     const int64_t total = (int64_t)NB * HW * (C / 4);
-    launch_pdl(gate_residual_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(h), ldh / 4, gate,
+    SFB_LAUNCH(gate_residual_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(h), ldh / 4, gate,
                                                                           reinterpret_cast<const float4*>(res), ldr / 4,
                                                                           reinterpret_cast<float4*>(out), ldo / 4, HW, C / 4, total);
     return check_launch("gate_residual");
@@ -858,7 +752,7 @@ extern "C" int sfb_plms_update(const float* x, const float* e0, const float* e1,
     SFB_REQUIRE(x && e0 && noise && x_prev, "plms_update: null pointer");
     int64_t blocks = (n + 255) / 256;
     if (blocks > 1024) blocks = 1024;
-    sfb::launch_pdl(sfb::plms_update_kernel, (unsigned)blocks, 256, 0, sfb::as_stream(stream), x, e0, e1, e2, e3, c0, c1, c2, c3, noise, alpha, sigma, alpha_next, c,
+    SFB_LAUNCH(sfb::plms_update_kernel, (unsigned)blocks, 256, 0, sfb::as_stream(stream), x, e0, e1, e2, e3, c0, c1, c2, c3, noise, alpha, sigma, alpha_next, c,
                                                                                  noise_scale, clip, x_prev, x0_out, e_out, n);
     return sfb::check_launch("plms_update");
 }

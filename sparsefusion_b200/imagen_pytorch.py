@@ -280,6 +280,8 @@ class Unet(nn.Module):
             _register(self, name, nn.Parameter(torch.empty(shape)))
         self.reset_parameters()
         self._plan = None  # packed weights etc., rebuilt lazily
+        self.use_arena = True      # split-K conv outputs from one zero-filled buffer per evaluation (ops.ZeroArena)
+        self._arena_floats = {}    # (nb, h, w) -> floats, measured on the first evaluation of that shape
 
     # ------------------------------------------------------------------------------------------ parameters
     @torch.no_grad()
@@ -370,12 +372,13 @@ class Unet(nn.Module):
                                accumulate=accumulate)
 
     def _linear_rows(self, name, x, bias=True, round_out=False):
-        """token projection [.., K] -> [.., O]: fp32 GEMV for few rows, tensor cores otherwise"""
+        """token projection [.., K] -> [.., O]: fp32 GEMV for a handful of rows, tensor cores (swap-AB tile: the rows are the N side) from 16 rows up --
+        in the replayed graph the 8-row GEMV tile costs 13.8 us per projection of the 4x4 stage's 16 tokens, the tcgen05 path ~5 us"""
         pl = self._plan
         w = pl['P'][name + '.weight']
         b = pl['P'].get(name + '.bias') if bias else None
         rows = x.numel() // x.shape[-1]
-        if rows <= 32 or (name + '.weight') not in pl['packed']:
+        if rows < 16 or (name + '.weight') not in pl['packed']:
             return ops.linear_small(x, w.reshape(w.shape[0], -1), b, round_to_tf32=round_out)
         return ops.linear_tc(x, pl['packed'][name + '.weight'], w.shape[0], bias=b)
 
@@ -463,82 +466,91 @@ class Unet(nn.Module):
         P = self._plan['P']
         nb, _, hh, ww = x.shape
         dev = x.device
-        with torch.cuda.device(dev):
-            # cat(cond_images * keep_mask, x) -> NHWC (imagen_pytorch.py:1496-1504); prob 0 keeps, prob 1 drops everything
-            cin = self.channels + self.cond_images_channels
-            xin = torch.zeros(nb, hh, ww, cin, dtype=torch.float32, device=dev)
-            if exists(cond_images):
-                assert cond_images.shape[1] == self.cond_images_channels
-                if cond_images.shape[-1] != ww:
-                    cond_images = torch.nn.functional.interpolate(cond_images, ww, mode='nearest')
-                if cond_drop_prob == 0.:
-                    ops.nchw_to_nhwc(cond_images.float(), xin, 0, True)
-                elif cond_drop_prob != 1.:
-                    keep = (torch.zeros((nb,), device=dev).float().uniform_(0, 1) < (1 - cond_drop_prob)).view(nb, 1, 1, 1)
-                    ops.nchw_to_nhwc(cond_images.float() * keep, xin, 0, True)
-            ops.nchw_to_nhwc(x.float(), xin, self.cond_images_channels, True)
-            # CrossEmbedLayer: three convolutions write adjacent channel slices (:1040-1042)
-            h0 = torch.empty(nb, hh, ww, self.dim, dtype=torch.float32, device=dev)
-            o = 0
-            for i, k in enumerate(self.kernel_sizes):
-                co = P[f'init_conv.convs.{i}.weight'].shape[0]
-                self._conv(f'init_conv.convs.{i}', xin, k, 1, (k - 1) // 2, out=h0[..., o:o + co])
-                o += co
-            xcur = h0
-            if taps is not None:
-                taps['init_conv'] = xcur
-            # time conditioning (:1517-1522, :1600-1604), fp32 GEMVs
-            four = ops.time_fourier(time.float().contiguous(), P['to_time_hiddens.0.weights'])
-            th = ops.linear_small(four, P['to_time_hiddens.1.weight'], P['to_time_hiddens.1.bias'], post=1)
-            tokens = ops.linear_small(th, P['to_time_tokens.0.weight'], P['to_time_tokens.0.bias']).view(nb, self.num_time_tokens, self.cond_dim)
-            t = ops.linear_small(th, P['to_time_cond.0.weight'], P['to_time_cond.0.bias'])
-            c = ops.layernorm(tokens, P['norm_cond.weight'], P['norm_cond.bias'], round_to_tf32=False)
-            film_all = ops.linear_small(t, self._plan['film_w'], self._plan['film_b'], pre=1)  # every block's SiLU->Linear time MLP at once
-            if taps is not None:
-                taps['t'], taps['c'] = t, c
+        # split-K destinations: one zero-filled arena per evaluation (ops.ZeroArena); the first evaluation of a shape only measures it
+        need = self._arena_floats.get((nb, hh, ww)) if self.use_arena else None
+        arena = ops.ArenaMeter() if (need is None and self.use_arena) else (ops.ZeroArena(need, dev) if need is not None else None)
+        with torch.cuda.device(dev), ops.use_arena(arena):
+            y = self._forward_nhwc(x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev)
+        if isinstance(arena, ops.ArenaMeter):
+            self._arena_floats[(nb, hh, ww)] = arena.floats
+        return y
 
-            n = len(self.dim_mults)
-            hiddens: List[torch.Tensor] = []
-            for i in range(n):
-                xcur = self._resnet(f'downs.{i}.1', xcur, film_all, c, taps)
-                for j in range(self.num_resnet_blocks[i]):
-                    xcur = self._resnet(f'downs.{i}.2.{j}', xcur, film_all, None, taps)
-                    hiddens.append(xcur)
-                if self.layer_attns[i]:
-                    xcur = self._transformer(f'downs.{i}.3', xcur, c)
-                    if taps is not None:
-                        taps[f'downs.{i}.3'] = xcur
+    def _forward_nhwc(self, x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev):
+        # cat(cond_images * keep_mask, x) -> NHWC (imagen_pytorch.py:1496-1504); prob 0 keeps, prob 1 drops everything
+        cin = self.channels + self.cond_images_channels
+        xin = torch.zeros(nb, hh, ww, cin, dtype=torch.float32, device=dev)
+        if exists(cond_images):
+            assert cond_images.shape[1] == self.cond_images_channels
+            if cond_images.shape[-1] != ww:
+                cond_images = torch.nn.functional.interpolate(cond_images, ww, mode='nearest')
+            if cond_drop_prob == 0.:
+                ops.nchw_to_nhwc(cond_images.float(), xin, 0, True)
+            elif cond_drop_prob != 1.:
+                keep = (torch.zeros((nb,), device=dev).float().uniform_(0, 1) < (1 - cond_drop_prob)).view(nb, 1, 1, 1)
+                ops.nchw_to_nhwc(cond_images.float() * keep, xin, 0, True)
+        ops.nchw_to_nhwc(x.float(), xin, self.cond_images_channels, True)
+        # CrossEmbedLayer: three convolutions write adjacent channel slices (:1040-1042)
+        h0 = torch.empty(nb, hh, ww, self.dim, dtype=torch.float32, device=dev)
+        o = 0
+        for i, k in enumerate(self.kernel_sizes):
+            co = P[f'init_conv.convs.{i}.weight'].shape[0]
+            self._conv(f'init_conv.convs.{i}', xin, k, 1, (k - 1) // 2, out=h0[..., o:o + co])
+            o += co
+        xcur = h0
+        if taps is not None:
+            taps['init_conv'] = xcur
+        # time conditioning (:1517-1522, :1600-1604), fp32 GEMVs
+        four = ops.time_fourier(time.float().contiguous(), P['to_time_hiddens.0.weights'])
+        th = ops.linear_small(four, P['to_time_hiddens.1.weight'], P['to_time_hiddens.1.bias'], post=1)
+        tokens = ops.linear_small(th, P['to_time_tokens.0.weight'], P['to_time_tokens.0.bias']).view(nb, self.num_time_tokens, self.cond_dim)
+        t = ops.linear_small(th, P['to_time_cond.0.weight'], P['to_time_cond.0.bias'])
+        c = ops.layernorm(tokens, P['norm_cond.weight'], P['norm_cond.bias'], round_to_tf32=False)
+        film_all = ops.linear_small(t, self._plan['film_w'], self._plan['film_b'], pre=1)  # every block's SiLU->Linear time MLP at once
+        if taps is not None:
+            taps['t'], taps['c'] = t, c
+
+        n = len(self.dim_mults)
+        hiddens: List[torch.Tensor] = []
+        for i in range(n):
+            xcur = self._resnet(f'downs.{i}.1', xcur, film_all, c, taps)
+            for j in range(self.num_resnet_blocks[i]):
+                xcur = self._resnet(f'downs.{i}.2.{j}', xcur, film_all, None, taps)
                 hiddens.append(xcur)
-                if i < n - 1:
-                    xcur = self._conv(f'downs.{i}.4', xcur, 4, 2, 1)
-                else:  # Parallel(conv3x3, conv1x1) summed (:1322)
-                    y = self._conv(f'downs.{i}.4.fns.0', xcur, 3, 1, 1)
-                    xcur = self._conv(f'downs.{i}.4.fns.1', xcur, 1, 1, 0, out=y, accumulate=True)
+            if self.layer_attns[i]:
+                xcur = self._transformer(f'downs.{i}.3', xcur, c)
                 if taps is not None:
-                    taps[f'downs.{i}.4'] = xcur
-
-            xcur = self._resnet('mid_block1', xcur, film_all, c, taps)
-            xcur = self._self_attn('mid_attn.fn.fn', xcur, None)
+                    taps[f'downs.{i}.3'] = xcur
+            hiddens.append(xcur)
+            if i < n - 1:
+                xcur = self._conv(f'downs.{i}.4', xcur, 4, 2, 1)
+            else:  # Parallel(conv3x3, conv1x1) summed (:1322)
+                y = self._conv(f'downs.{i}.4.fns.0', xcur, 3, 1, 1)
+                xcur = self._conv(f'downs.{i}.4.fns.1', xcur, 1, 1, 0, out=y, accumulate=True)
             if taps is not None:
-                taps['mid_attn'] = xcur
-            xcur = self._resnet('mid_block2', xcur, film_all, c, taps)
+                taps[f'downs.{i}.4'] = xcur
 
-            for i in range(n):
-                ri = n - 1 - i
-                xcur = self._resnet(f'ups.{i}.0', ops.concat2(xcur, hiddens.pop(), self.skip_connect_scale), film_all, c, taps)
-                for j in range(self.num_resnet_blocks[ri]):
-                    xcur = self._resnet(f'ups.{i}.1.{j}', ops.concat2(xcur, hiddens.pop(), self.skip_connect_scale), film_all, None, taps)
-                if self.layer_attns[ri]:
-                    xcur = self._transformer(f'ups.{i}.2', xcur, c)
-                    if taps is not None:
-                        taps[f'ups.{i}.2'] = xcur
-                if i < n - 1:
-                    xcur = ops.pixel_shuffle_silu(self._conv(f'ups.{i}.3.net.0', xcur, 1))
-                    if taps is not None:
-                        taps[f'ups.{i}.3'] = xcur
-            xcur = self._resnet('final_res_block', xcur, film_all, None, taps)
-            y = self._conv('final_conv', xcur, 3, 1, 1)
-            return ops.nhwc_to_nchw(y)
+        xcur = self._resnet('mid_block1', xcur, film_all, c, taps)
+        xcur = self._self_attn('mid_attn.fn.fn', xcur, None)
+        if taps is not None:
+            taps['mid_attn'] = xcur
+        xcur = self._resnet('mid_block2', xcur, film_all, c, taps)
+
+        for i in range(n):
+            ri = n - 1 - i
+            xcur = self._resnet(f'ups.{i}.0', ops.concat2(xcur, hiddens.pop(), self.skip_connect_scale), film_all, c, taps)
+            for j in range(self.num_resnet_blocks[ri]):
+                xcur = self._resnet(f'ups.{i}.1.{j}', ops.concat2(xcur, hiddens.pop(), self.skip_connect_scale), film_all, None, taps)
+            if self.layer_attns[ri]:
+                xcur = self._transformer(f'ups.{i}.2', xcur, c)
+                if taps is not None:
+                    taps[f'ups.{i}.2'] = xcur
+            if i < n - 1:
+                xcur = ops.pixel_shuffle_silu(self._conv(f'ups.{i}.3.net.0', xcur, 1))
+                if taps is not None:
+                    taps[f'ups.{i}.3'] = xcur
+        xcur = self._resnet('final_res_block', xcur, film_all, None, taps)
+        y = self._conv('final_conv', xcur, 3, 1, 1)
+        return ops.nhwc_to_nchw(y)
 
 
 class UnetGraph:

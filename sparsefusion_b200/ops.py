@@ -82,6 +82,68 @@ def _rows_meta(t: torch.Tensor) -> Tuple[int, int, int]:
 
 
 # --------------------------------------------------------------------------------------------- conv / linear on tensor cores
+# --------------------------------------------------------------------------------------------- split-K output arena
+# The weight-streaming convolutions split K over up to 148 CTAs and meet in fp32 red.global.add, so their destination must start from
+# zero.  One cudaMemset node per convolution costs ~2.3 us inside the replayed UNet graph (and breaks the programmatic-dependent-launch
+# edge in front of the convolution); with an arena all conv outputs of one UNet evaluation are carved out of ONE buffer that is
+# zero-filled once at the start of the evaluation, and the convolutions run in "accumulate" mode.
+class ZeroArena:
+    def __init__(self, floats: int, device):
+        self.buf = torch.zeros(max(int(floats), 1), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.off + n > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 63) // 64 * 64          # 256-byte granules keep every tensor 16-byte aligned for TMA
+        return t
+
+
+class ArenaMeter:
+    """first evaluation of a shape: count the floats an arena would have to hold"""
+
+    def __init__(self):
+        self.floats = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        self.floats += (n + 63) // 64 * 64
+        return None
+
+
+_arena = None
+
+
+class use_arena:
+    def __init__(self, arena):
+        self.arena = arena
+
+    def __enter__(self):
+        global _arena
+        self.prev, _arena = _arena, self.arena
+        return self.arena
+
+    def __exit__(self, *exc):
+        global _arena
+        _arena = self.prev
+        return False
+
+
+def _conv_out(shape, device):
+    """(tensor, pre-zeroed?)"""
+    if _arena is not None:
+        t = _arena.take(shape)
+        if t is not None:
+            return t, True
+    return torch.empty(*shape, dtype=torch.float32, device=device), False
+
+
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 accumulate: bool = False, splits: int = 0, bn: int = 0) -> torch.Tensor:
@@ -89,7 +151,8 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw:
     ho = (h + 2 * pad - kh) // stride + 1
     wo = (w + 2 * pad - kw) // stride + 1
     if out is None:
-        out = torch.empty(nb, ho, wo, cout, dtype=torch.float32, device=x.device)
+        out, zeroed = _conv_out((nb, ho, wo, cout), x.device)
+        accumulate = accumulate or zeroed           # pre-zeroed destination: reduce straight into it, no memset node
     onb, oh, ow, oc, ldo = _nhwc_meta(out)
     assert (onb, oh, ow, oc) == (nb, ho, wo, cout), f'out shape {tuple(out.shape)} != {(nb, ho, wo, cout)}'
     assert w_packed.shape == (cout, kh * kw * ((cin + 31) // 32 * 32)), 'packed weight shape mismatch'
@@ -107,15 +170,16 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=N
     """nn.Linear on the tensor cores: rows [T, K] are treated as T 1x1 'images'"""
     t, k, ld = _rows_meta(x)
     x4 = x.as_strided((t, 1, 1, k), (ld, ld, ld, 1))
+    zeroed = False
     if out is None:
-        out = torch.empty(*x.shape[:-1], out_features, dtype=torch.float32, device=x.device)
+        out, zeroed = _conv_out((*x.shape[:-1], out_features), x.device)
     to, co, ldo = _rows_meta(out)
     o4 = out.as_strided((t, 1, 1, out_features), (ldo, ldo, ldo, 1))
     r4 = None
     if residual is not None:
         tr, cr, ldr = _rows_meta(residual)
         r4 = residual.as_strided((t, 1, 1, out_features), (ldr, ldr, ldr, 1))
-    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4)
+    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed)
     return out
 
 

@@ -56,3 +56,27 @@ def test_v2_matches_reference_and_v1(case):
     y0 = torch.ones_like(ref)
     ops.conv2d_nhwc(x, wp, cout, k, k, stride, pad, out=y0, accumulate=True)
     assert ((y0 - (_ref(x, wt, None, stride, pad) + 1)).norm() / ref.norm()).item() < 1e-5
+
+
+def test_tensor_core_reads_tf32_by_truncation():
+    """Experiment recorded as a test: feeding the un-masked fp32 word as the 'hi' operand (variant 3) must give bit-identical
+    results to the explicitly masked operand (variant 2) if -- and only if -- kind::tf32 ignores the 13 low mantissa bits."""
+    from sparsefusion_b200 import _lib as lib, ops
+    ops.set_precision('tf32x3')
+    g = torch.Generator(device='cuda').manual_seed(5)
+    same = []
+    for (nb, h, w, cin, cout, k) in [(1, 4, 4, 1024, 1024, 3), (1, 32, 32, 256, 256, 3), (1, 8, 8, 512, 512, 1)]:
+        x = torch.randn(nb, h, w, cin, device='cuda', generator=g)
+        wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k) ** 0.5
+        wp = ops.pack_conv_weight(wt)
+        out = {}
+        for v in (2, 3):
+            lib.call('sfb_conv_set_variant', v)
+            try:
+                out[v] = ops.conv2d_nhwc(x, wp, cout, k, k, 1, k // 2, splits=1)
+            finally:
+                lib.call('sfb_conv_set_variant', 2)
+        same.append(bool(torch.equal(out[2], out[3])))
+        rel = ((out[3] - out[2]).norm() / out[2].norm()).item()
+        print(f'raw-hi vs masked-hi {(nb, h, w, cin, cout, k)}: bit-identical={same[-1]} rel diff {rel:.3e}')
+    print('TENSOR CORE TF32 READ IS A TRUNCATION' if all(same) else 'tensor core tf32 read is NOT a plain truncation')

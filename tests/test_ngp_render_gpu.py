@@ -39,7 +39,16 @@ def test_state_dict_keys_match_reference_checkpoint_layout():
     assert {'density_grid', 'density_bitfield', 'step_counter'} <= set(net2.state_dict().keys())
 
 
-def test_field_forward_backward_vs_oracle():
+@pytest.fixture(params=[0x7fffffff, 0], ids=['wgrad-tcgen05', 'wgrad-simt'])
+def wgrad_path(request):
+    """both implementations of the MLP weight gradients (sfb_set_fusion bit 0)"""
+    from sparsefusion_b200 import _lib as lib
+    lib.call('sfb_set_fusion', request.param)
+    yield request.param
+    lib.call('sfb_set_fusion', 0x7fffffff)
+
+
+def test_field_forward_backward_vs_oracle(wgrad_path):
     from oracle import ngp_oracle as no
     net, p, _ = _net()
     rng = np.random.default_rng(3)

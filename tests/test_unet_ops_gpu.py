@@ -36,19 +36,10 @@ def test_pixel_shuffle_silu():
     _close(ops.pixel_shuffle_silu(y), ref, 1e-5)
 
 
-@pytest.fixture(params=[0x7fffffff, 0], ids=['fused', 'multikernel'])
-def fusion(request):
-    """both code paths of the operators that have a single-launch cluster variant (sfb_set_fusion)"""
-    from sparsefusion_b200 import _lib as lib
-    lib.call('sfb_set_fusion', request.param)
-    yield request.param
-    lib.call('sfb_set_fusion', 0x7fffffff)
-
-
 @pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
                                    (2, 5, 7, 96, 8), (1, 64, 64, 512, 8)])
 @pytest.mark.parametrize('film', [False, True])
-def test_groupnorm_film_silu(shape, film, fusion):
+def test_groupnorm_film_silu(shape, film):
     from sparsefusion_b200 import ops
     nb, h, w, c, g = shape
     x = torch.randn(nb, h, w, c, device='cuda') * 3 + 0.7
@@ -99,9 +90,10 @@ def test_time_fourier():
 
 
 @pytest.mark.parametrize('nc', [0, 2])
-def test_mq_attention(nc):
+@pytest.mark.parametrize('n,heads,dh', [(16, 8, 64), (64, 4, 32), (37, 3, 128), (400, 2, 64)])   # the last one exceeds the smem-staged kernel
+def test_mq_attention(nc, n, heads, dh):
     from sparsefusion_b200 import ops
-    b, n, heads, dh = 2, 16, 8, 64
+    b = 2
     q = torch.randn(b, n, heads * dh, device='cuda')
     kv = torch.randn(b, n, 2 * dh, device='cuda')
     null_kv = torch.randn(2, dh, device='cuda')
@@ -139,7 +131,7 @@ def test_cross_attention():
 
 
 @pytest.mark.parametrize('shape', [(2, 16, 16, 256), (1, 32, 32, 256), (1, 4, 4, 1024), (3, 8, 8, 1024), (2, 3, 1, 64), (1, 16, 16, 512), (1, 8, 8, 96)])
-def test_gca_pool_and_gate_residual(shape, fusion):
+def test_gca_pool_and_gate_residual(shape):
     from sparsefusion_b200 import ops
     nb, h, w, c = shape
     x = torch.randn(nb, h, w, c, device='cuda') * 2

@@ -69,6 +69,65 @@ def unet_bench(out):
     ops.set_precision('tf32x3')
 
 
+def unet_trace(out):
+    """in-situ chain cost of every UNet kernel inside the replayed graph (sfb_trace_begin): stamp[i+1] - stamp[i]"""
+    global FLUSH
+    import ctypes
+    import collections
+    from sparsefusion_b200 import _lib
+    if 'nopdl' in sys.argv:
+        _lib.call('sfb_set_pdl', 0)
+    if 'nofuse' in sys.argv:
+        _lib.call('sfb_set_fusion', 0)
+    from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
+    unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
+                layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
+    torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)
+    ops.set_precision('tf32x3')
+    unet.prepare()
+    x, cond, t = torch.randn(1, 4, 32, 32, device='cuda'), torch.randn(1, 256, 32, 32, device='cuda'), torch.full((1,), 0.3, device='cuda')
+    runner = UnetGraph(unet)
+    for _ in range(3):
+        runner(x, t, cond)
+    torch.cuda.synchronize()
+    cap = 4096
+    buf = torch.zeros(cap + 1, dtype=torch.int64, device='cuda')
+    _lib.call('sfb_trace_begin', buf.data_ptr(), cap)
+    unet.forward(x, t, cond_images=cond)            # names in launch order (same sequence as the captured graph)
+    torch.cuda.synchronize()
+    n_eager = int(buf[0])
+    nbuf = ctypes.create_string_buffer(1 << 20)
+    _lib.load().sfb_trace_names(nbuf, len(nbuf))
+    names = nbuf.value.decode().split('\n')[:-1]
+    runs = []
+    for _ in range(5):
+        if FLUSH is None:
+            FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+        FLUSH.zero_()
+        buf.zero_()
+        torch.cuda.synchronize()
+        runner(x, t, cond)
+        torch.cuda.synchronize()
+        k = int(buf[0])
+        runs.append(buf[1:1 + k].cpu().numpy().astype('int64'))
+    _lib.call('sfb_trace_end')
+    import numpy as np
+    st = runs[-1]
+    assert len(st) == len(names) == n_eager, (len(st), len(names), n_eager)
+    iv = np.median(np.stack([np.diff(r) for r in runs[1:]]), axis=0) / 1e3      # us, median over replays
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for nm, d in zip(names[:-1], iv):
+        agg[nm][0] += 1
+        agg[nm][1] += float(d)
+    total = float(iv.sum())
+    print(f'trace: {len(names)} kernels, first-to-last stamp {total:.1f} us', flush=True)
+    for nm, (c, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f'  {tt:9.1f} us  {c:4d} x {tt / c:7.2f}  {nm}')
+    tag = '_'.join(['trace'] + [a for a in sys.argv[1:] if a in ('nopdl', 'nofuse')])
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(dict(names=names, interval_us=[round(float(v), 3) for v in iv], total_us=total), open(os.path.join(ROOT, 'gpurun_out', tag + '.json'), 'w'))
+
+
 def vae_bench(out):
     from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
     torch.backends.cudnn.allow_tf32 = True
@@ -115,6 +174,8 @@ def main():
         unet_bench(out)
     if 'render' in sys.argv or len(sys.argv) == 1:
         render_bench(out)
+    if 'trace' in sys.argv:
+        unet_trace(out)
     if 'vae' in sys.argv or len(sys.argv) == 1:
         vae_bench(out)
     if len(sys.argv) > 1 and 'conv' not in sys.argv:
