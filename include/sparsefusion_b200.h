@@ -43,7 +43,8 @@ int sfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int sfb_set_precision(int mode);
 int sfb_get_precision(void);
 /* programmatic dependent launch of the UNet kernels (default on): each kernel may be scheduled while its predecessor drains and
- * waits (griddepcontrol.wait) before touching global memory.  0 restores plain stream-ordered launches (A/B measurement). */
+ * waits (griddepcontrol.wait) before touching global memory.  Bit 0 clear restores plain stream-ordered launches; bit 1 set stops requesting
+ * the maximum shared-memory carve-out for kernels launched for the first time afterwards (A/B measurement). */
 int sfb_set_pdl(int on);
 /* in-situ tracer for the UNet kernels: while a trace is open every traced kernel appends %globaltimer (ns) to device_buf right after its
  * griddepcontrol.wait (device_buf[0] = number of stamps, device_buf[1..capacity] = stamps; zero it before each run) and the host records
@@ -52,6 +53,10 @@ int sfb_set_pdl(int on);
 int sfb_trace_begin(unsigned long long* device_buf, unsigned int capacity);
 int sfb_trace_end(void);
 int sfb_trace_names(char* out, int capacity);
+/* phase stamps inside the tcgen05 convolution (CTA 0 of every launch): device_buf[0] = launches seen, device_buf[1 + 8*i + p] = %globaltimer
+ * of phase p (0 entry, 1 prologue done, 2 dependency wait returned, 3 first stage converted, 4 last MMA committed, 5 accumulator complete,
+ * 6 epilogue done) of launch i < capacity.  NULL unbinds. */
+int sfb_conv_phase_trace(unsigned long long* device_buf, unsigned int capacity);
 /* optional code paths (default all on): bit 0 = the NGP MLP weight gradients run as 3xTF32 tcgen05 GEMMs over the feature-major tapes
  * (cleared: the fp32 SIMT outer-product kernel).  Both agree to fp32 rounding; the switch exists for A/B measurement and tests. */
 int sfb_set_fusion(int mask);

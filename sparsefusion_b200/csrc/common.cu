@@ -40,6 +40,24 @@ int precision_mode() { return t_precision_override >= 0 ? t_precision_override :
 int set_precision_override(int m) { const int old = t_precision_override; t_precision_override = m; return old; }
 void set_precision_mode(int m) { g_precision = m; }
 
+static std::atomic<int> g_carveout{1};
+void prefer_smem(const void* kernel) {
+    static std::unordered_set<const void*> done;
+    static std::mutex mu;
+    if (!g_carveout.load()) return;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static std::atomic<int> g_pad_smem{0};
+size_t pad_smem(const void* kernel, size_t smem) {
+    constexpr size_t kPad = 150 * 1024;
+    if (!g_pad_smem.load() || smem >= kPad) return smem;
+    static std::unordered_set<const void*> done;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPad);
+    return kPad;
+}
 static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load() != 0; }
 void set_pdl(int on) { g_pdl.store(on != 0); }
@@ -81,7 +99,7 @@ int sfb_set_precision(int mode) {
     return SFB_OK;
 }
 int sfb_get_precision(void) { return sfb::precision_mode(); }
-int sfb_set_pdl(int on) { sfb::set_pdl(on); return SFB_OK; }
+int sfb_set_pdl(int on) { sfb::set_pdl(on & 1); sfb::g_carveout.store((on & 2) ? 0 : 1); sfb::g_pad_smem.store((on & 4) ? 1 : 0); return SFB_OK; }
 int sfb_trace_begin(unsigned long long* device_buf, unsigned int capacity) {
     {
         std::lock_guard<std::mutex> lock(sfb::g_trace_mu);
@@ -100,6 +118,11 @@ int sfb_trace_end(void) {
     }
     sfb::trace_bind_unet_ops(nullptr, 0);
     sfb::trace_bind_conv_v2(nullptr, 0);
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+}
+int sfb_conv_phase_trace(unsigned long long* device_buf, unsigned int capacity) {
+    sfb::phase_bind_conv_v2(device_buf, capacity);
     SFB_CUDA(cudaGetLastError());
     return SFB_OK;
 }

@@ -30,7 +30,7 @@ struct Conv2Cfg {
     static constexpr int kStagesSmem = (200 * 1024) / kStageBytes;
     static constexpr int kStagesTmem = (512 - kABase) / 64;   // 32 hi + 32 lo columns per stage
     static constexpr int kStages = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024 + 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024 + 512 + 512;   // stages | barriers 512 | bias 1024 | pixel index 512 | alignment slack
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -55,6 +55,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// Phase tracer (sfb_conv_phase_trace): CTA (0,0,0) of every launch stamps %globaltimer at 7 points into buf[1 + 8*launch + phase]:
+//   0 kernel entry, 1 prologue done (barriers, TMEM alloc), 2 griddepcontrol.wait returned, 3 first stage converted (MMA can start),
+//   4 last MMA committed, 5 accumulator complete (epilogue starts), 6 epilogue done.
+static __device__ unsigned long long* t_phase_buf = nullptr;
+static __device__ unsigned int t_phase_cap = 0;
+__device__ __forceinline__ void phase_mark(unsigned int slot, int phase) {
+    if (slot != 0xffffffffu) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        t_phase_buf[1 + (size_t)slot * 8 + phase] = t;
+    }
+}
+
 // SWAP == false: M-side = 128 output pixels (tmA), N-side = BN output channels (tmB).
 // SWAP == true : M-side = 128 output channels (tmB), N-side = BN output pixels (tmA, box {32, TW, TH, TN} with TW*TH*TN == BN).
 template <int BN, bool SWAP>
@@ -70,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     uint64_t* tmem_full_bar = conv_bar + S;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* bias_s = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 512);   // up to 256 floats
+    int* pix_s = reinterpret_cast<int*>(smem + S * Cfg::kStageBytes + 512 + 1024);   // SWAP: linear output pixel of tile column j, or -1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
@@ -80,7 +94,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     const int ke = (int)(((int64_t)p.k_iters * (blockIdx.z + 1)) / p.splits);
     const int niter = ke - kb;
 
+    uint32_t* phase_slot = tmem_holder + 1;
     if (threadIdx.x == 0) {
+        unsigned int slot = 0xffffffffu;
+        if (t_phase_buf != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+            const unsigned long long sidx = atomicAdd(t_phase_buf, 1ull);
+            if (sidx < t_phase_cap) slot = (unsigned int)sidx;
+        }
+        *phase_slot = slot;
+        phase_mark(slot, 0);
         for (int i = 0; i < S; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); tc::mbar_init(&conv_bar[i], 4); }
         tc::mbar_init(tmem_full_bar, 1);
         tc::fence_mbar_init();
@@ -94,6 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_holder;
+    const uint32_t pslot = *phase_slot;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -121,12 +144,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             // PDL: the weights do not depend on the previous kernel -- the first S stages of weight tiles stream in while it drains;
             // the activation tiles of those stages follow once griddepcontrol.wait returns.
             const int pre = niter < S ? niter : S;
+            phase_mark(pslot, 1);
             pdl_trigger();
             for (int it = 0; it < pre; ++it) {
                 tc::mbar_expect_tx(&full_bar[it], kABytes + Cfg::kNBytes);
                 load_weights(it);
             }
             pdl_wait();
+            phase_mark(pslot, 2);
             trace_mark();
             for (int it = 0; it < pre; ++it) load_acts(it);
             for (int it = pre; it < niter; ++it) {
@@ -147,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 tc::mbar_wait(&conv_bar[s], ph);
                 tc::fence_after_sync();
+                if (it == 0) phase_mark(pslot, 3);
                 const uint32_t b_hi = tc::smem_u32(smem + s * Cfg::kStageBytes + kABytes), b_lo = b_hi + Cfg::kNBytes;
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::kABase + 64 * s), a_lo = a_hi + 32;
 #pragma unroll
@@ -159,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 tc::umma_commit(&empty_bar[s]);
             }
             tc::umma_commit(tmem_full_bar);
+            phase_mark(pslot, 4);
         }
     } else {
         // ------------------------------------------------------------ converter + epilogue (warps 2..5)
@@ -169,6 +196,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
         for (int i = et; i < nb; i += 128) {
             const int c = cout0 + i;
             bias_s[i] = (p.bias != nullptr && blockIdx.z == 0 && c < p.Cout) ? p.bias[c] : 0.f;
+        }
+        if (SWAP && et < BN) {
+            const int tw = et % p.TW, th = (et / p.TW) % p.TH, tn = et / (p.TW * p.TH);
+            const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+            pix_s[et] = (n < p.NB && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         pdl_wait();   // residual reads / output writes below must see the previous kernel's results (bias is a constant)
@@ -225,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
         const bool use_red = (p.splits > 1) || (p.accumulate != 0);
         tc::mbar_wait(tmem_full_bar, 0);
         tc::fence_after_sync();
+        if (et == 0) phase_mark(pslot, 5);
         if (!SWAP) {
             const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
             const int n = n0 + tn, h = h0 + th, w = w0 + tw;
@@ -275,14 +308,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 for (int e = 0; e < 32; ++e) {
                     const int pj = j * 32 + e;                          // pixel index inside the tile (uniform across the warp)
                     if (pj < BN) {
-                        const int tw = pj % p.TW, th = (pj / p.TW) % p.TH, tn = pj / (p.TW * p.TH);
-                        const int n = n0 + tn, h = h0 + th, w = w0 + tw;
-                        if (cvalid && n < p.NB && h < p.Ho && w < p.Wo) {
-                            const int64_t pix = (int64_t)((int64_t)n * p.Ho + h) * p.Wo + w;
+                        const int pix = pix_s[pj];
+                        if (cvalid && pix >= 0) {
                             float x = __uint_as_float(v[e]) + bv;
-                            if (add_res) x += __ldg(p.residual + pix * p.ldr + c);
-                            float* dst = p.out + pix * p.ldo + c;
-                            if (use_red) atomicAdd(dst, x);
+                            if (add_res) x += __ldg(p.residual + (int64_t)pix * p.ldr + c);
+                            float* dst = p.out + (int64_t)pix * p.ldo + c;
+                            if (use_red) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(x) : "memory");
                             else *dst = x;
                         }
                     }
@@ -290,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             }
         }
     }
+    if (threadIdx.x == 64) phase_mark(pslot, 6);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) {
@@ -314,6 +346,10 @@ static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
 }
 
 void trace_bind_conv_v2(unsigned long long* buf, unsigned int cap) { trace_bind_this_tu(buf, cap); }
+void phase_bind_conv_v2(unsigned long long* buf, unsigned int cap) {
+    cudaMemcpyToSymbol(t_phase_buf, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(t_phase_cap, &cap, sizeof(cap));
+}
 
 int launch_conv_v2(const ConvGemmParams& p, int BN, bool swap, dim3 grid, cudaStream_t st) {
     if (swap) {

@@ -58,7 +58,8 @@ class PLMSSampler:
         if self.use_cuda_graph and cond_scale == 1:
             if self._graph is None or self._graph.unet is not unet:
                 self._graph = UnetGraph(unet)
-            return self._graph(x, log_snr, cond_images).clone()
+            # cond_images is fixed for the whole sampling run: its share of init_conv is evaluated by the first call only
+            return self._graph(x, log_snr, cond_images, new_cond=(self.last_unet_calls == 1)).clone()
         return unet.forward_with_cond_scale(x, log_snr, cond_images=cond_images, cond_scale=cond_scale)
 
     @torch.no_grad()

@@ -110,3 +110,28 @@ def test_plms_sampler_vs_reference_trajectories(golden_dir):
         print(f'PLMS max_thres={max_thres}: {sampler.last_unet_calls} UNet calls, rel vs reference {rel:.3e}')
         assert rel < 5e-3   # error compounds over the sampler's steps; each eps is within 1e-3
         assert torch.allclose(x_noisy.cpu(), torch.from_numpy(g[f'x_noisy_{key}']), atol=1e-5)
+
+
+@pytest.mark.parametrize('which', ['SMALL', 'FULL'])
+def test_cond_feature_cache_and_graph_match_plain_forward(which):
+    """init_conv split into a cached cond_images share + the 4-channel x share (Unet.precompute_cond) and the two-graph runner
+    must reproduce the plain forward to fp32 summation-order noise; a stale cache must not be used when new_cond is left at True."""
+    from oracle import unet_oracle as uo
+    from sparsefusion_b200.imagen_pytorch import UnetGraph
+    cfg = getattr(uo, which)
+    unet, _ = _build(cfg)
+    x, cond = _inputs(cfg, 1, 11)
+    x2, cond2 = _inputs(cfg, 1, 12)
+    x, cond, x2, cond2 = x.cuda(), cond.cuda(), x2.cuda(), cond2.cuda()
+    t = torch.full((1,), 0.37, device='cuda')
+    ref = unet.forward(x, t, cond_images=cond)
+    feat = unet.precompute_cond(cond)
+    got = unet.forward(x, t, cond_features=feat)
+    assert _rel(got, ref) < 2e-5, _rel(got, ref)
+    runner = UnetGraph(unet)
+    assert _rel(runner(x, t, cond).clone(), ref) < 2e-5
+    ref2 = unet.forward(x2, t, cond_images=cond)
+    assert _rel(runner(x2, t, cond, new_cond=False).clone(), ref2) < 2e-5        # same conditioning, cached share reused
+    ref3 = unet.forward(x2, t, cond_images=cond2)
+    assert _rel(runner(x2, t, cond2).clone(), ref3) < 2e-5                       # new conditioning, default recomputes
+    assert _rel(ref3, ref2) > 1e-3                                               # (the two conditionings really differ)

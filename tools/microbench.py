@@ -77,8 +77,10 @@ def unet_trace(out):
     from sparsefusion_b200 import _lib
     if 'nopdl' in sys.argv:
         _lib.call('sfb_set_pdl', 0)
-    if 'nofuse' in sys.argv:
-        _lib.call('sfb_set_fusion', 0)
+    if 'nocarve' in sys.argv:
+        _lib.call('sfb_set_pdl', 3)
+    if 'padsmem' in sys.argv:
+        _lib.call('sfb_set_pdl', 5)
     from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
     unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
@@ -92,28 +94,33 @@ def unet_trace(out):
     torch.cuda.synchronize()
     cap = 4096
     buf = torch.zeros(cap + 1, dtype=torch.int64, device='cuda')
+    pbuf = torch.zeros(1 + 8 * 128, dtype=torch.int64, device='cuda')
     _lib.call('sfb_trace_begin', buf.data_ptr(), cap)
-    unet.forward(x, t, cond_images=cond)            # names in launch order (same sequence as the captured graph)
+    unet.forward(x, t, cond_features=unet.precompute_cond(cond))            # names in launch order (same sequence as the captured main graph)
     torch.cuda.synchronize()
     n_eager = int(buf[0])
     nbuf = ctypes.create_string_buffer(1 << 20)
     _lib.load().sfb_trace_names(nbuf, len(nbuf))
     names = nbuf.value.decode().split('\n')[:-1]
+    _lib.call('sfb_conv_phase_trace', pbuf.data_ptr(), 128)
     runs = []
     for _ in range(5):
         if FLUSH is None:
             FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
         FLUSH.zero_()
         buf.zero_()
+        pbuf.zero_()
         torch.cuda.synchronize()
-        runner(x, t, cond)
+        runner(x, t, cond, new_cond=False)
         torch.cuda.synchronize()
         k = int(buf[0])
         runs.append(buf[1:1 + k].cpu().numpy().astype('int64'))
     _lib.call('sfb_trace_end')
+    _lib.call('sfb_conv_phase_trace', None, 0)
     import numpy as np
+    names = names[-int(buf[0]):]                     # the eager pass also recorded precompute_cond's kernels first
     st = runs[-1]
-    assert len(st) == len(names) == n_eager, (len(st), len(names), n_eager)
+    assert len(st) == len(names) <= n_eager, (len(st), len(names), n_eager)
     iv = np.median(np.stack([np.diff(r) for r in runs[1:]]), axis=0) / 1e3      # us, median over replays
     agg = collections.defaultdict(lambda: [0, 0.0])
     for nm, d in zip(names[:-1], iv):
@@ -123,9 +130,49 @@ def unet_trace(out):
     print(f'trace: {len(names)} kernels, first-to-last stamp {total:.1f} us', flush=True)
     for nm, (c, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f'  {tt:9.1f} us  {c:4d} x {tt / c:7.2f}  {nm}')
-    tag = '_'.join(['trace'] + [a for a in sys.argv[1:] if a in ('nopdl', 'nofuse')])
+    tag = '_'.join(['trace'] + [a for a in sys.argv[1:] if a in ('nopdl', 'nocarve', 'padsmem')])
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(dict(names=names, interval_us=[round(float(v), 3) for v in iv], total_us=total), open(os.path.join(ROOT, 'gpurun_out', tag + '.json'), 'w'))
+    npc = int(pbuf[0])
+    json.dump(dict(names=names, interval_us=[round(float(v), 3) for v in iv], total_us=total, stamps=[int(v) for v in runs[-1]],
+                   conv_phase_stamps=pbuf[1:1 + 8 * npc].cpu().numpy().reshape(npc, 8).tolist()), open(os.path.join(ROOT, 'gpurun_out', tag + '.json'), 'w'))
+
+
+def conv_phases(out):
+    """where a tcgen05 conv launch spends its time (sfb_conv_phase_trace): medians over 20 launches, cold L2, arena-style accumulate mode"""
+    global FLUSH
+    import numpy as np
+    from sparsefusion_b200 import _lib
+    ops.set_precision('tf32x3')
+    if FLUSH is None:
+        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    cap = 64
+    buf = torch.zeros(1 + 8 * cap, dtype=torch.int64, device='cuda')
+    print('phases (us): prologue | dep-wait | first-stage | mainloop | drain | epilogue | total   [grid]')
+    rows = []
+    for name, h, cin, cout, k, stride in conv_cases():
+        x = torch.randn(1, h, h, cin, device='cuda')
+        w = ops.pack_conv_weight(torch.randn(cout, cin, k, k, device='cuda') / (cin * k * k) ** 0.5)
+        b = torch.zeros(cout, device='cuda')
+        pad = (k - 1) // 2 if stride == 1 else 1
+        y = ops.conv2d_nhwc(x, w, cout, k, k, stride, pad, bias=b)
+        y.zero_()
+        _lib.call('sfb_conv_phase_trace', buf.data_ptr(), cap)
+        buf.zero_()
+        n = 20
+        for _ in range(n):
+            FLUSH.zero_()
+            ops.conv2d_nhwc(x, w, cout, k, k, stride, pad, bias=b, out=y, accumulate=True)
+        torch.cuda.synchronize()
+        _lib.call('sfb_conv_phase_trace', None, 0)
+        st = buf[1:1 + 8 * n].cpu().numpy().reshape(n, 8)[:, :7].astype('float64')
+        d = np.median(np.diff(st, axis=1), axis=0) / 1e3
+        tot = float(np.median(st[:, 6] - st[:, 0]) / 1e3)
+        rec = dict(name=name, hw=h, cin=cin, cout=cout, k=k, prologue=round(float(d[0]), 2), dep_wait=round(float(d[1]), 2), first_stage=round(float(d[2]), 2),
+                   mainloop=round(float(d[3]), 2), drain=round(float(d[4]), 2), epilogue=round(float(d[5]), 2), total=round(tot, 2), weight_mb=round(w.numel() * 4 / 1e6, 2))
+        rows.append(rec)
+        print(f"{name:12s} {d[0]:6.2f} | {d[1]:6.2f} | {d[2]:6.2f} | {d[3]:6.2f} | {d[4]:6.2f} | {d[5]:6.2f} | {tot:6.2f}   W {rec['weight_mb']:6.2f} MB", flush=True)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'conv_phases.json'), 'w'), indent=1)
 
 
 def vae_bench(out):
@@ -176,6 +223,8 @@ def main():
         render_bench(out)
     if 'trace' in sys.argv:
         unet_trace(out)
+    if 'phases' in sys.argv:
+        conv_phases(out)
     if 'vae' in sys.argv or len(sys.argv) == 1:
         vae_bench(out)
     if len(sys.argv) > 1 and 'conv' not in sys.argv:
