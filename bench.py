@@ -218,28 +218,74 @@ def run_gpu(args):
         x = torch.randn(1, 4, 32, 32, device=device)
         c = torch.randn(1, 256, 32, 32, device=device)
         t = torch.full((1,), 0.3, device=device)
+        feat = unet.precompute_cond(c)       # the sampler evaluates the conditioning map's share of init_conv once per run, not per evaluation
         for _ in range(2):
-            unet.forward(x, t, cond_images=c)
+            unet.forward(x, t, cond_features=feat)
         torch.cuda.synchronize()
+        import ctypes
+        tbuf = torch.zeros(4097, dtype=torch.int64, device=device)
+        _lib.call('sfb_trace_begin', tbuf.data_ptr(), 4096)     # kernel names in launch order (+ stamps) for the in-graph measurement below
+        unet.forward(x, t, cond_features=feat)
+        torch.cuda.synchronize()
+        nbuf = ctypes.create_string_buffer(1 << 20)
+        _lib.load().sfb_trace_names(nbuf, len(nbuf))
+        names = nbuf.value.decode().split('\n')[:-1]
         _lib.call('sfb_conv_prof_enable', 1)
         reps = 5
         for _ in range(reps):
             torch.cuda._sleep(int(2e7))   # ~10 ms of GPU idle-spin: the CPU enqueues the whole eager evaluation behind it, so the
-            unet.forward(x, t, cond_images=c)   # events around each conv launch measure kernel time, not CPU launch gaps
+            unet.forward(x, t, cond_features=feat)   # events around each conv launch measure kernel time, not CPU launch gaps
             torch.cuda.synchronize()
-        import ctypes
         tot, nl, wb, fl = ctypes.c_double(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
         _lib.load().sfb_conv_prof_collect(ctypes.byref(tot), ctypes.byref(nl), ctypes.byref(wb), ctypes.byref(fl))
         _lib.call('sfb_conv_prof_enable', 0)
         conv_ms_per_eval = tot.value / reps
         per_launch_us = 1e3 * tot.value / max(1, nl.value)
         achieved = (wb.value / reps) / (conv_ms_per_eval * 1e-3) / 1e9
-        roof = {'kernel': 'conv_gemm_tf32_kernel (tcgen05 implicit-GEMM conv/linear)', 'bound': 'hbm', 'achieved': round(achieved, 1),
+        # the same kernels inside the replayed CUDA graph of the timed region: %globaltimer stamp of every kernel right after its dependency
+        # wait (sfb_trace_begin); consecutive stamps = chain cost of a kernel, launch / dependency latency included
+        in_graph = None
+        runner = dist.sampler._graph
+        if runner is not None:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+            conv_us, all_us = [], []
+            for _ in range(5):
+                flush.zero_()
+                tbuf.zero_()
+                runner(x, t, c, new_cond=False)
+                torch.cuda.synchronize()
+                k = int(tbuf[0])
+                stamps = tbuf[1:1 + k].cpu().numpy().astype('int64')
+                if k != len(names):
+                    break
+                iv = np.diff(stamps) / 1e3
+                conv_us.append(float(sum(d for nm, d in zip(names[:-1], iv) if nm.startswith('conv_v2'))))
+                all_us.append(float(iv.sum()))
+            if conv_us:
+                cu, au = float(np.median(conv_us)), float(np.median(all_us))
+                n_conv = sum(1 for nm in names if nm.startswith('conv_v2'))
+                in_graph = {'kernels_per_eval': len(names), 'conv_launches_per_eval': n_conv, 'conv_us_per_eval': round(cu, 1),
+                            'eval_us_first_to_last_kernel': round(au, 1), 'achieved_GBps': round((wb.value / reps) / (cu * 1e-6) / 1e9, 1),
+                            'frac': round((wb.value / reps) / (cu * 1e-6) / 1e9 / pk['hbm_gbs'], 4)}
+        _lib.call('sfb_trace_end')
+        traffic = None
+        try:    # DRAM bytes per conv launch from the committed ncu --set full capture of this kernel (profiles/, tools/gpu_profile.sh)
+            import csv
+            prof = [f for f in sorted(os.listdir(os.path.join(ROOT, 'profiles'))) if f.endswith('_conv_full_ncu.csv')][-1]
+            rows = list(csv.DictReader(open(os.path.join(ROOT, 'profiles', prof))))
+            traffic = round(sum(float(r['dram_read_MB']) + float(r['dram_write_MB']) for r in rows) * 1e6 / len(rows))
+            traffic_src = f'profiles/{prof}: mean dram__bytes_read.sum + dram__bytes_write.sum over {len(rows)} conv launches of one UNet evaluation'
+        except Exception as e:   # noqa: BLE001
+            traffic_src = f'no ncu capture under profiles/ ({e})'
+        roof = {'kernel': 'conv_gemm_v2_kernel (tcgen05 3xTF32 implicit-GEMM conv/linear, weights streamed from HBM)', 'bound': 'hbm',
+                'achieved': round(achieved, 1),
                 'peak': pk['hbm_gbs'], 'peak_source': f'{pk_kind} MEASURED_PEAKS.json hbm_gbs (copy bandwidth)', 'unit': 'GB/s',
-                'frac': round(achieved / pk['hbm_gbs'], 4), 'traffic': None,
+                'frac': round(achieved / pk['hbm_gbs'], 4), 'traffic': traffic, 'traffic_source': traffic_src,
+                'algorithmic_bytes_per_launch': int(wb.value / max(1, nl.value)),
                 'algorithmic_bytes_per_eval': int(wb.value / reps), 'launches_per_eval': nl.value // reps,
                 'avg_launch_us': round(per_launch_us, 2), 'conv_ms_per_unet_eval': round(conv_ms_per_eval, 4),
                 'tensor_tflops_equiv': round((fl.value / reps) / (conv_ms_per_eval * 1e-3) / 1e12, 2),
+                'in_graph': in_graph,
                 'unet_eval_ms_in_timed_region': round(unet_ms / max(1, n_unet), 4), 'unet_evals_in_timed_region': n_unet,
                 'unet_share_of_step': round(unet_ms / ms, 4),
                 'note': 'B=1 UNet evaluation is weight-streaming bound (SURVEY §7): achieved = fp32 weight bytes of the conv/linear layers '
@@ -257,7 +303,7 @@ def run_gpu(args):
                'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, 7.46 MB NGP-gradient all-reduce per sub-step',
                           'unet_evals_per_step_mean': round(float(np.mean(n_calls)), 2) if n_calls else None,
                           'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
-                          'vae': 'torch (cuDNN, TF32) -- SURVEY §8f next row, not yet ported', 'lpips': 'excluded in every arm (un-vendored dependency)',
+                          'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'lpips': 'excluded in every arm (un-vendored dependency)',
                           'precision_mode': ops.get_precision()},
                'clocks': clk, 'gpu_launches': int(launches),
                'e2e': None if e2e_val is None else {'value': round(e2e_val, 4), 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

@@ -152,6 +152,11 @@ int sfb_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
 int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW,
                          int stride, int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                          int accumulate, int splits, int bn, void* stream);
+/* same with `pad` zeros before the first and `pad_after` after the last row / column: ldm's Downsample pads (0,1,0,1) in front of a
+ * stride-2 3x3 convolution (external/ldm/modules/diffusionmodules/model.py:73-75) */
+int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW,
+                             int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                             int accumulate, int splits, int bn, void* stream);
 int sfb_conv_weight_k(int Cin, int KH, int KW);
 /* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
 int sfb_conv_prof_enable(int on);
@@ -195,6 +200,10 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
 /* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW + 2*NB + 2 floats */
 int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
                  void* stream);
+/* VAE helpers.  softmax over the columns of every row of scale * x (ldm AttnBlock, model.py:183-190);
+ * nearest-neighbour x2 upsampling in NHWC (ldm Upsample, model.py:44-52). */
+int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream);
+int sfb_upsample2x_nhwc(const float* x, int64_t ldx, float* out, int64_t ldo, int NB, int H, int W, int C, void* stream);
 /* ResnetBlock tail (:727-729): out = h * gate[n][c] + res (gate NULL == 1) */
 int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const float* res, int64_t ldr, float* out, int64_t ldo, int NB,
                            int HW, int C, void* stream);

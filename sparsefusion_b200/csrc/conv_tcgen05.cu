@@ -374,13 +374,22 @@ int sfb_conv_weight_k(int Cin, int KH, int KW) { return KH * KW * ((Cin + 31) / 
 int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW, int stride,
                          int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate, int splits, int bn,
                          void* stream) {
+    return sfb_conv2d_nhwc_tf32_pad(x, NB, H, W, Cin, ldx, w_packed, Cout, KH, KW, stride, pad, pad, bias, residual, ldr, out, ldo, accumulate, splits, bn,
+                                    stream);
+}
+
+int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW, int stride,
+                             int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate,
+                             int splits, int bn, void* stream) {
     SFB_REQUIRE(x && w_packed && out, "conv2d_nhwc_tf32: null pointer");
     SFB_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_nhwc_tf32: empty shape");
     SFB_REQUIRE(stride == 1 || stride == 2, "conv2d_nhwc_tf32: stride must be 1 or 2");
     SFB_REQUIRE(Cin % 4 == 0 && ldx % 4 == 0 && ldx >= Cin, "conv2d_nhwc_tf32: Cin and ldx must be multiples of 4 floats (TMA 16-byte strides)");
     SFB_REQUIRE(Cout % 4 == 0 && ldo % 4 == 0, "conv2d_nhwc_tf32: Cout and ldo must be multiples of 4");
     SFB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv2d_nhwc_tf32: pointers must be 16-byte aligned");
-    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+    SFB_REQUIRE(pad >= 0 && pad_after >= 0, "conv2d_nhwc_tf32: negative padding");
+    // `pad` zeros before row/column 0, `pad_after` after the last one; both are TMA out-of-bounds zero fill, only the output extent differs
+    const int Ho = (H + pad + pad_after - KH) / stride + 1, Wo = (W + pad + pad_after - KW) / stride + 1;
     SFB_REQUIRE(Ho > 0 && Wo > 0, "conv2d_nhwc_tf32: empty output");
     if (stride == 2) SFB_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv2d_nhwc_tf32: stride 2 needs even H and W");
 

@@ -556,6 +556,49 @@ __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v
     }
 }
 
+// ------------------------------------------------------------------------------------ VAE helpers (ldm AttnBlock / Upsample)
+// y[r][:] = softmax(scale * x[r][:]) over `cols` columns; one CTA per row (ldm model.py:183-190: single-head attention over h*w tokens)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int cols,
+                                                          float scale) {
+    pdl_sync();
+    __shared__ float red[8];
+    const float* xr = x + (int64_t)blockIdx.x * ldx;
+    float* yr = y + (int64_t)blockIdx.x * ldy;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, xr[c] * scale);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sm = 0.f;
+    for (int c = threadIdx.x; c < cols; c += 256) sm += expf(xr[c] * scale - mx);
+    sm = warp_sum(sm);
+    if (lane == 0) red[warp] = sm;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float inv = 1.f / tot;
+    for (int c = threadIdx.x; c < cols; c += 256) yr[c] = expf(xr[c] * scale - mx) * inv;
+}
+
+// nearest-neighbour x2 upsampling, NHWC: out[n][2h+i][2w+j][c] = x[n][h][w][c]   (ldm model.py:44-52)
+__global__ void upsample2x_kernel(const float4* __restrict__ x, int64_t ldx_v, float4* __restrict__ out, int64_t ldo_v, int H, int W, int Cv, int64_t total) {
+    pdl_sync();
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cv);
+        int64_t t = idx / Cv;
+        const int ow = (int)(t % (2 * W)); t /= (2 * W);
+        const int oh = (int)(t % (2 * H));
+        const int64_t n = t / (2 * H);
+        out[((n * 2 * H + oh) * (int64_t)(2 * W) + ow) * ldo_v + c] = __ldg(x + ((n * H + (oh >> 1)) * W + (ow >> 1)) * ldx_v + c);
+    }
+}
+
 void trace_bind_unet_ops(unsigned long long* buf, unsigned int cap) { trace_bind_this_tu(buf, cap); }
 
 static inline int ew_blocks(int64_t total, int threads = 256) {
@@ -703,6 +746,23 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     SFB_REQUIRE(sm <= 48 * 1024, "gca_pool: image too large for the single-pass pooling kernel");
     SFB_LAUNCH(gca_pool_kernel, dim3(ceil_div(C, kGcaCols), NB), 256, sm, st, x, ldx, logits_ws, pooled, HW, C);
     return check_launch("gca_pool(pool)");
+}
+
+int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream) {
+    SFB_REQUIRE(x && y && rows >= 0 && cols > 0, "softmax_rows: null pointer or empty row");
+    if (rows == 0) return SFB_OK;
+    SFB_LAUNCH(softmax_rows_kernel, rows, 256, 0, as_stream(stream), x, ldx, y, ldy, cols, scale);
+    return check_launch("softmax_rows");
+}
+
+int sfb_upsample2x_nhwc(const float* x, int64_t ldx, float* out, int64_t ldo, int NB, int H, int W, int C, void* stream) {
+    SFB_REQUIRE(x && out, "upsample2x_nhwc: null pointer");
+    SFB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "upsample2x_nhwc: channel counts must be multiples of 4");
+    const int64_t total = (int64_t)NB * 4 * H * W * (C / 4);
+    if (total == 0) return SFB_OK;
+    SFB_LAUNCH(upsample2x_kernel, ew_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(x), ldx / 4, reinterpret_cast<float4*>(out),
+               ldo / 4, H, W, C / 4, total);
+    return check_launch("upsample2x_nhwc");
 }
 
 int sfb_gate_residual_nhwc(const float* h, int64_t ldh, const float* gate, const float* res, int64_t ldr, float* out, int64_t ldo, int NB, int HW,

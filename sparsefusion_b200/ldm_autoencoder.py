@@ -2,12 +2,18 @@
 (external/ldm/models/autoencoder.py:285-333, external/ldm/modules/diffusionmodules/model.py:82-142,150-203,368-568,
 external/ldm/modules/distributions/distributions.py:24-62, config external/ldm/configs/sd-vae.yaml).
 
-STATUS: this is SURVEY.md §8f "next" row #1, not yet ported to the sm_100a conv engine.  It is kept in plain torch
-(cuDNN) so that a distillation step can run end to end with all of the reference's in-loop work present
-(``vae.encode(...).mode()`` at sparsefusion/distillation.py:299 and ``vae.decode(...)`` at :309, both under no_grad);
-DESIGN.md lists it as out of the B200-native scope of this round.  Same module tree and state_dict keys as the
-reference (``encoder.*``, ``decoder.*``, ``quant_conv``, ``post_quant_conv``), without the pytorch_lightning / taming
-base classes the reference drags in.
+SURVEY.md §8f "next" row #1.  Same module tree and state_dict keys as the reference (``encoder.*``, ``decoder.*``,
+``quant_conv``, ``post_quant_conv``), without the pytorch_lightning / taming base classes the reference drags in.
+
+Two execution paths behind ``encode`` / ``decode`` (both inference-only in the loop: ``vae.encode(...).mode()`` at
+sparsefusion/distillation.py:299 and ``vae.decode(...)`` at :309 run under no_grad):
+
+* CUDA tensors -> the sm_100a engine (``_Sm100Engine`` below): NHWC activations, every convolution / 1x1 projection / attention
+  matmul on the tcgen05 3xTF32 implicit-GEMM kernel (``ops.conv2d_nhwc``), GroupNorm(32)+swish fused in one pass over the
+  data, nearest upsampling and the row softmax as small kernels.  No cuDNN, no torch matmul.  ``engine='torch'`` restores the
+  plain-torch modules on the GPU for A/B tests.
+* CPU tensors -> the plain torch modules below.  That path exists as the *reference mirror* (tests, bench.py's cpu_baseline);
+  the product path is CUDA and raises if libsparsefusion_b200.so is missing.
 """
 from __future__ import annotations
 
@@ -172,19 +178,146 @@ class DiagonalGaussianDistribution:
         return self.mean + self.std * torch.randn_like(self.mean)
 
 
+class _Sm100Engine:
+    """Encoder / Decoder forward on the sm_100a operators (NHWC, 3xTF32 tensor cores).  Weights are packed once (``prepare``)."""
+
+    GROUPS, EPS = 32, 1e-6
+
+    def __init__(self, vae: 'AutoencoderKL'):
+        from . import ops
+        self.ops = ops
+        self.vae = vae
+        P = {n: p.detach() for n, p in vae.named_parameters()}
+        if next(iter(P.values())).device.type != 'cuda':
+            raise RuntimeError('the sm_100a VAE engine needs CUDA parameters')
+        self.P, self.W, self.B = P, {}, {}
+        for n, p in P.items():
+            if n.endswith('.weight') and p.dim() == 4:
+                base = n[:-len('.weight')]
+                w, b = p, P.get(base + '.bias')
+                if w.shape[0] % 4:                                   # decoder.conv_out: 3 output channels -> pad to 4 (TMA / vector stores)
+                    padc = 4 - w.shape[0] % 4
+                    w = torch.cat((w, w.new_zeros(padc, *w.shape[1:])), dim=0)
+                    b = torch.cat((b, b.new_zeros(padc))) if b is not None else None
+                self.W[base] = ops.pack_conv_weight(w)
+                self.B[base] = None if b is None else b.float().contiguous()
+
+    # ---- building blocks
+    def conv(self, name, x, k, stride=1, pad=None, pad_after=None, residual=None):
+        w = self.W[name]
+        pad = (k - 1) // 2 if pad is None else pad
+        return self.ops.conv2d_nhwc(x, w, w.shape[0], k, k, stride, pad, bias=self.B[name], residual=residual, pad_after=pad_after)
+
+    def gn(self, name, x, swish):
+        return self.ops.groupnorm(x, self.GROUPS, self.P[name + '.weight'], self.P[name + '.bias'], None, swish, eps=self.EPS)
+
+    def resnet(self, pfx, x):                                         # model.py:82-142
+        h = self.conv(pfx + '.conv1', self.gn(pfx + '.norm1', x, True), 3)
+        h = self.gn(pfx + '.norm2', h, True)
+        sc = self.conv(pfx + '.nin_shortcut', x, 1) if (pfx + '.nin_shortcut') in self.W else x
+        return self.conv(pfx + '.conv2', h, 3, residual=sc)
+
+    def attn(self, pfx, x):                                           # model.py:150-203, single head over h*w tokens
+        ops = self.ops
+        nb, hh, ww, c = x.shape
+        n = hh * ww
+        if n % 32 or c % 32:
+            raise NotImplementedError('sm_100a VAE attention needs h*w and channels to be multiples of 32')
+        hn = self.gn(pfx + '.norm', x, False)
+        out = torch.empty_like(x)
+        wv = self.P[pfx + '.v.weight'].reshape(c, c)
+        for b in range(nb):
+            rows = hn[b].reshape(n, c)
+            q = ops.linear_tc(rows, self.W[pfx + '.q'], c, bias=self.B[pfx + '.q'])
+            k = ops.linear_tc(rows, self.W[pfx + '.k'], c, bias=self.B[pfx + '.k'])
+            scores = ops.linear_tc(q, k, n)                           # q k^T: the keys are the GEMM's [Cout = n][K = c] operand
+            probs = ops.softmax_rows(scores, scale=float(c) ** -0.5)
+            vt = ops.linear_tc(wv, rows, n)                           # (W_v h^T) = v^T without bias: [c][n], the K-major operand of P.V
+            o = ops.linear_tc(probs, vt, c, bias=self.B[pfx + '.v'])   # rows of P sum to 1, so v's bias is added once per output row
+            ops.linear_tc(o, self.W[pfx + '.proj_out'], c, bias=self.B[pfx + '.proj_out'], residual=x[b].reshape(n, c), out=out[b].reshape(n, c))
+        return out
+
+    # ---- Encoder.forward (model.py:368-460) + quant_conv (autoencoder.py:311-315)
+    def encode_moments(self, x):
+        ops, enc = self.ops, self.vae.encoder
+        nb, cin, hh, ww = x.shape
+        xin = torch.zeros(nb, hh, ww, (cin + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+        ops.nchw_to_nhwc(x.float(), xin, 0)
+        h = self.conv('encoder.conv_in', xin, 3)
+        for i in range(enc.num_resolutions):
+            for j in range(enc.num_res_blocks):
+                h = self.resnet(f'encoder.down.{i}.block.{j}', h)
+            if i != enc.num_resolutions - 1:
+                h = self.conv(f'encoder.down.{i}.downsample.conv', h, 3, stride=2, pad=0, pad_after=1)      # F.pad (0,1,0,1), model.py:73-75
+        h = self.resnet('encoder.mid.block_1', h)
+        h = self.attn('encoder.mid.attn_1', h)
+        h = self.resnet('encoder.mid.block_2', h)
+        h = self.conv('encoder.conv_out', self.gn('encoder.norm_out', h, True), 3)
+        return ops.nhwc_to_nchw(self.conv('quant_conv', h, 1))
+
+    # ---- post_quant_conv + Decoder.forward (model.py:462-568)
+    def decode(self, z):
+        ops, dec = self.ops, self.vae.decoder
+        nb, cz, hh, ww = z.shape
+        zin = torch.zeros(nb, hh, ww, (cz + 3) // 4 * 4, dtype=torch.float32, device=z.device)
+        ops.nchw_to_nhwc(z.float(), zin, 0)
+        h = self.conv('decoder.conv_in', self.conv('post_quant_conv', zin, 1), 3)
+        h = self.resnet('decoder.mid.block_1', h)
+        h = self.attn('decoder.mid.attn_1', h)
+        h = self.resnet('decoder.mid.block_2', h)
+        for i in reversed(range(dec.num_resolutions)):
+            for j in range(dec.num_res_blocks + 1):
+                h = self.resnet(f'decoder.up.{i}.block.{j}', h)
+            if i != 0:
+                h = self.conv(f'decoder.up.{i}.upsample.conv', ops.upsample2x(h), 3)
+        y = self.conv('decoder.conv_out', self.gn('decoder.norm_out', h, True), 3)
+        out_ch = self.P['decoder.conv_out.weight'].shape[0]
+        return ops.nhwc_to_nchw(y[..., :out_ch])
+
+
 class AutoencoderKL(nn.Module):
-    def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=4, embed_dim=4):
+    def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=4, embed_dim=4, engine='sm100'):
         super().__init__()
         self.encoder = Encoder(ch, ch_mult, num_res_blocks, in_channels, z_channels, True)
         self.decoder = Decoder(ch, out_ch, ch_mult, num_res_blocks, z_channels)
         self.quant_conv = nn.Conv2d(2 * z_channels, 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, z_channels, 1)
         self.embed_dim = embed_dim
+        assert engine in ('sm100', 'torch')
+        self.engine = engine        # CUDA inputs: 'sm100' = the tcgen05 engine, 'torch' = plain torch modules (A/B tests only)
+        self._sm100 = None
+
+    def prepare(self):
+        """(re)pack the weights for the sm_100a engine; call again after loading a checkpoint or switching ops.set_precision"""
+        self._sm100 = _Sm100Engine(self)
+        return self
+
+    def _engine_for(self, t):
+        if not t.is_cuda or self.engine != 'sm100':
+            return None
+        if torch.is_grad_enabled() and (t.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError('the sm_100a VAE engine is inference-only (the distillation loop calls the VAE under no_grad): wrap the call in '
+                               "torch.no_grad() or construct AutoencoderKL(engine='torch')")
+        if self._sm100 is None:
+            self.prepare()
+        return self._sm100
+
+    def load_state_dict(self, *args, **kwargs):
+        self._sm100 = None
+        return super().load_state_dict(*args, **kwargs)
 
     def encode(self, x):
+        eng = self._engine_for(x)
+        if eng is not None:
+            with torch.no_grad(), torch.cuda.device(x.device):
+                return DiagonalGaussianDistribution(eng.encode_moments(x))
         return DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
 
     def decode(self, z):
+        eng = self._engine_for(z)
+        if eng is not None:
+            with torch.no_grad(), torch.cuda.device(z.device):
+                return eng.decode(z)
         return self.decoder(self.post_quant_conv(z))
 
     def forward(self, x, sample_posterior=True):

@@ -146,10 +146,12 @@ def _conv_out(shape, device):
 
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                accumulate: bool = False, splits: int = 0, bn: int = 0) -> torch.Tensor:
+                accumulate: bool = False, splits: int = 0, bn: int = 0, pad_after: Optional[int] = None) -> torch.Tensor:
     nb, h, w, cin, ldx = _nhwc_meta(x)
-    ho = (h + 2 * pad - kh) // stride + 1
-    wo = (w + 2 * pad - kw) // stride + 1
+    if pad_after is None:
+        pad_after = pad
+    ho = (h + pad + pad_after - kh) // stride + 1
+    wo = (w + pad + pad_after - kw) // stride + 1
     if out is None:
         out, zeroed = _conv_out((nb, ho, wo, cout), x.device)
         accumulate = accumulate or zeroed           # pre-zeroed destination: reduce straight into it, no memset node
@@ -160,8 +162,8 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw:
     if residual is not None:
         rnb, rh, rw, rc, ldr = _nhwc_meta(residual)
         assert (rnb, rh, rw, rc) == (nb, ho, wo, cout)
-    lib.call('sfb_conv2d_nhwc_tf32', x.data_ptr(), nb, h, w, cin, ldx,
-             lib.fptr(w_packed, 'w_packed'), cout, kh, kw, stride, pad, lib.fptr(bias, 'bias'),
+    lib.call('sfb_conv2d_nhwc_tf32_pad', x.data_ptr(), nb, h, w, cin, ldx,
+             lib.fptr(w_packed, 'w_packed'), cout, kh, kw, stride, pad, pad_after, lib.fptr(bias, 'bias'),
              None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
     return out
 
@@ -180,6 +182,22 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=N
         tr, cr, ldr = _rows_meta(residual)
         r4 = residual.as_strided((t, 1, 1, out_features), (ldr, ldr, ldr, 1))
     conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed)
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * x) over the last dim of a [rows, cols] matrix (row stride free)"""
+    t, c, ld = _rows_meta(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    lib.call('sfb_softmax_rows', x.data_ptr(), ld, out.data_ptr(), _rows_meta(out)[2], t, c, float(scale), lib.stream())
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    nb, h, w, c, ldx = _nhwc_meta(x)
+    out = torch.empty(nb, 2 * h, 2 * w, c, dtype=torch.float32, device=x.device)
+    lib.call('sfb_upsample2x_nhwc', x.data_ptr(), ldx, out.data_ptr(), c, nb, h, w, c, lib.stream())
     return out
 
 

@@ -183,6 +183,11 @@ def vae_bench(out):
     img = torch.rand(1, 3, 256, 256, device='cuda')
     z = torch.randn(1, 4, 32, 32, device='cuda')
     with torch.no_grad():
+        out['vae_sm100'] = dict(encode_ms=round(timeit(lambda: vae.encode(img).mode(), iters=10, flush=False), 3),
+                                decode_ms=round(timeit(lambda: vae.decode(z), iters=10, flush=False), 3))
+        print('vae sm100', out['vae_sm100'], flush=True)
+    vae.engine = 'torch'
+    with torch.no_grad():
         enc = timeit(lambda: vae.encode(img).mode(), iters=10, flush=False)
         dec = timeit(lambda: vae.decode(z), iters=10, flush=False)
         vcl = vae.to(memory_format=torch.channels_last)
