@@ -122,15 +122,25 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     const int p0 = (int)(((int64_t)HW * sl) / S), p1 = (int)(((int64_t)HW * (sl + 1)) / S);
     const float* base = x + ((int64_t)n * HW + p0) * ldx + g * Cg;
     double s = 0.0, ss = 0.0;
-    const int64_t total4 = (int64_t)(p1 - p0) * Cg4;
-    for (int64_t i = threadIdx.x; i < total4; i += blockDim.x) {
-        const int64_t pix = i / Cg4;
-        const int c4 = (int)(i - pix * Cg4);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * ldx) + c4);
-        const float a = v.x + v.y + v.z + v.w;
-        const float b = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        s += (double)a;
-        ss += (double)b;
+    if ((Cg & 3) == 0) {
+        const int64_t total4 = (int64_t)(p1 - p0) * Cg4;
+        for (int64_t i = threadIdx.x; i < total4; i += blockDim.x) {
+            const int64_t pix = i / Cg4;
+            const int c4 = (int)(i - pix * Cg4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * ldx) + c4);
+            const float a = v.x + v.y + v.z + v.w;
+            const float b = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            s += (double)a;
+            ss += (double)b;
+        }
+    } else {   // narrow groups (1..3 channels, or not a multiple of 4): scalar loads
+        const int64_t total = (int64_t)(p1 - p0) * Cg;
+        for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const int64_t pix = i / Cg;
+            const float v = __ldg(base + pix * ldx + (int)(i - pix * Cg));
+            s += (double)v;
+            ss += (double)(v * v);
+        }
     }
     __shared__ double sh_s[8], sh_ss[8];
     s = warp_sum_d(s);
@@ -181,12 +191,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = i / C4;
         const int c = (int)(i - pix * C4) * 4;
-        const float2 st = st_sh[c / Cg];
+        const float2 s0 = st_sh[c / Cg], s1 = st_sh[(c + 1) / Cg], s2 = st_sh[(c + 2) / Cg], s3 = st_sh[(c + 3) / Cg];   // equal when 4 | Cg
         const float4 v = __ldg(reinterpret_cast<const float4*>(xn + pix * ldx + c));
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-        float o[4] = {(v.x - st.x) * st.y * ga.x + be.x, (v.y - st.x) * st.y * ga.y + be.y, (v.z - st.x) * st.y * ga.z + be.z,
-                      (v.w - st.x) * st.y * ga.w + be.w};
+        float o[4] = {(v.x - s0.x) * s0.y * ga.x + be.x, (v.y - s1.x) * s1.y * ga.y + be.y, (v.z - s2.x) * s2.y * ga.z + be.z,
+                      (v.w - s3.x) * s3.y * ga.w + be.w};
         if (film) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + c));
             const float4 sh = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + C + c));
@@ -651,7 +661,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
                        int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy, void* stream) {
     SFB_REQUIRE(x && gamma && beta && stats_ws && y, "groupnorm_nhwc: null pointer");
     SFB_REQUIRE(((uintptr_t)stats_ws & 15) == 0, "groupnorm_nhwc: workspace must be 16-byte aligned");
-    SFB_REQUIRE(C % G == 0 && (C / G) % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "groupnorm_nhwc: channels per group must be a multiple of 4");
+    SFB_REQUIRE(C % G == 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "groupnorm_nhwc: C must be a multiple of the group count and of 4");
     cudaStream_t st = as_stream(stream);
     // workspace: 16-byte aligned fp64 partials [NB*G*S][2] (the leading (mean, rstd) slots of the old layout stay unused)
     SFB_REQUIRE(G <= kGnMaxGroups, "groupnorm_nhwc: at most 32 groups");

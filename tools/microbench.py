@@ -137,6 +137,47 @@ def unet_trace(out):
                    conv_phase_stamps=pbuf[1:1 + 8 * npc].cpu().numpy().reshape(npc, 8).tolist()), open(os.path.join(ROOT, 'gpurun_out', tag + '.json'), 'w'))
 
 
+def vae_trace(out):
+    """chain cost of every kernel of one VAE decode / encode (eager launches queued behind a GPU spin so the stamps show GPU time, not CPU gaps)"""
+    import ctypes
+    import collections
+    import numpy as np
+    from sparsefusion_b200 import _lib
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    vae = AutoencoderKL().cuda().eval()
+    img = torch.rand(1, 3, 256, 256, device='cuda')
+    z = torch.randn(1, 4, 32, 32, device='cuda')
+    cap = 4096
+    buf = torch.zeros(cap + 1, dtype=torch.int64, device='cuda')
+    for what, fn in (('decode', lambda: vae.decode(z)), ('encode', lambda: vae.encode(img).mode())):
+        with torch.no_grad():
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            _lib.call('sfb_trace_begin', buf.data_ptr(), cap)
+            buf.zero_()
+            torch.cuda._sleep(int(6e7))
+            fn()
+            torch.cuda.synchronize()
+        nbuf = ctypes.create_string_buffer(1 << 20)
+        _lib.load().sfb_trace_names(nbuf, len(nbuf))
+        names = nbuf.value.decode().split('\n')[:-1]
+        _lib.call('sfb_trace_end')
+        k = int(buf[0])
+        st = buf[1:1 + k].cpu().numpy().astype('int64')
+        iv = np.diff(st) / 1e3
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for nm, d in zip(names[:-1], iv):
+            agg[nm][0] += 1
+            agg[nm][1] += float(d)
+        print(f'vae {what}: {len(names)} kernels, first-to-last {iv.sum():.1f} us')
+        for nm, (c, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f'  {tt:9.1f} us  {c:4d} x {tt / c:8.2f}  {nm}')
+        top = sorted(zip(iv, range(len(iv))), reverse=True)[:12]
+        print('  longest:', [(round(float(d), 1), names[i]) for d, i in top])
+        json.dump(dict(names=names, interval_us=[round(float(v), 2) for v in iv]), open(os.path.join(ROOT, 'gpurun_out', f'trace_vae_{what}.json'), 'w'))
+
+
 def conv_phases(out):
     """where a tcgen05 conv launch spends its time (sfb_conv_phase_trace): medians over 20 launches, cold L2, arena-style accumulate mode"""
     global FLUSH
@@ -230,6 +271,8 @@ def main():
         unet_trace(out)
     if 'phases' in sys.argv:
         conv_phases(out)
+    if 'vaetrace' in sys.argv:
+        vae_trace(out)
     if 'vae' in sys.argv or len(sys.argv) == 1:
         vae_bench(out)
     if len(sys.argv) > 1 and 'conv' not in sys.argv:
