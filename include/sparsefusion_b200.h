@@ -157,6 +157,13 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
 int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW,
                              int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                              int accumulate, int splits, int bn, void* stream);
+/* same with an optional pre-split copy of the weights: w_hi_lo = [2][Cout][sfb_conv_weight_k] with hi = bits & 0xFFFFE000 and lo = w - hi, or
+ * NULL.  Used by the tensor-bound launches (more than 64 output pixels) in 3xTF32 mode: hi and lo tiles are TMA-loaded side by side and the
+ * operand converter only handles the activation tile.  Weight-streaming launches (swap-AB) keep reading w_packed: they are HBM-bound and the
+ * split copy would double their traffic. */
+int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH,
+                            int KW, int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                            int accumulate, int splits, int bn, void* stream);
 int sfb_conv_weight_k(int Cin, int KH, int KW);
 /* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
 int sfb_conv_prof_enable(int on);
@@ -200,6 +207,10 @@ int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, 
 /* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW + 2*NB + 2 floats */
 int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
                  void* stream);
+/* the same tail with GlobalContext's last layer folded in: gate[n][c] = sigmoid(b2[c] + w2[c][:] . hid[n][:]) (Conv2d(hidden, dim_out, 1) +
+ * Sigmoid, :929-933), out = h * gate + res.  hid [NB][Hd], w2 [C][Hd]. */
+int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, const float* w2, const float* b2, int Hd, const float* res, int64_t ldr,
+                               float* out, int64_t ldo, int NB, int HW, int C, void* stream);
 /* VAE helpers.  softmax over the columns of every row of scale * x (ldm AttnBlock, model.py:183-190);
  * nearest-neighbour x2 upsampling in NHWC (ldm Upsample, model.py:44-52). */
 int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream);

@@ -14,6 +14,7 @@ constexpr int kThreads = 192;
 struct alignas(64) ConvGemmParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    CUtensorMap tmBlo;      // pre-split weights (non-swap v2 only): tmB = hi = w & 0xFFFFE000, tmBlo = lo = w - hi
     float* out;
     const float* bias;
     const float* residual;  // optional [pixel][ldr] tensor added to the result (by split 0)
@@ -26,6 +27,7 @@ struct alignas(64) ConvGemmParams {
     int32_t KH, KW, pad, stride;
     int32_t k_iters, splits;
     int32_t accumulate;
+    int32_t presplit;       // tmB / tmBlo hold (hi, lo) of the weights: the converter leaves the N-side tile alone
     int32_t raw_hi;         // experiment (variant 3): feed the un-masked fp32 word as the "hi" tensor-core operand (is the hardware's tf32 read a truncation?)
 };
 

@@ -381,6 +381,13 @@ int sfb_conv2d_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t 
 int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, int Cout, int KH, int KW, int stride,
                              int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate,
                              int splits, int bn, void* stream) {
+    return sfb_conv2d_nhwc_tf32_ex(x, NB, H, W, Cin, ldx, w_packed, nullptr, Cout, KH, KW, stride, pad, pad_after, bias, residual, ldr, out, ldo, accumulate,
+                                   splits, bn, stream);
+}
+
+int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
+                            int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                            int accumulate, int splits, int bn, void* stream) {
     SFB_REQUIRE(x && w_packed && out, "conv2d_nhwc_tf32: null pointer");
     SFB_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_nhwc_tf32: empty shape");
     SFB_REQUIRE(stride == 1 || stride == 2, "conv2d_nhwc_tf32: stride must be 1 or 2");
@@ -473,7 +480,16 @@ int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int6
         const uint64_t dims[4] = {ktot, (uint64_t)Cout, 1, 1};
         const uint64_t strides[3] = {ktot * 4, 0, 0};
         const uint32_t boxB[4] = {32u, (uint32_t)w_rows, 1, 1};
-        if (int rc = make_map(&p.tmB, w_packed, dims, strides, boxB, 2)) return rc;
+        const bool presplit = (w_hi_lo != nullptr) && v2 && !swap && (swap || BN <= 128);
+        p.presplit = presplit ? 1 : 0;
+        if (presplit) {
+            SFB_REQUIRE(((uintptr_t)w_hi_lo & 15) == 0, "conv2d_nhwc_tf32: w_hi_lo must be 16-byte aligned");
+            if (int rc = make_map(&p.tmB, w_hi_lo, dims, strides, boxB, 2)) return rc;
+            if (int rc = make_map(&p.tmBlo, w_hi_lo + (size_t)Cout * ktot, dims, strides, boxB, 2)) return rc;
+        } else {
+            if (int rc = make_map(&p.tmB, w_packed, dims, strides, boxB, 2)) return rc;
+            p.tmBlo = p.tmB;
+        }
     }
 
     if (splits > 1 && !accumulate) {

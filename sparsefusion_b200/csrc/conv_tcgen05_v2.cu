@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ symbol, so the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-    uint64_t* empty_bar = full_bar + S;
+    // two arrival barriers per stage -- weights and activations -- so that the converter can process the weight tiles of the first stages while
+    // the activations do not exist yet (they are loaded after griddepcontrol.wait; the weights before)
+    uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    uint64_t* afull_bar = wfull_bar + S;
+    uint64_t* empty_bar = afull_bar + S;
     uint64_t* conv_bar = empty_bar + S;
     uint64_t* tmem_full_bar = conv_bar + S;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -103,7 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
         }
         *phase_slot = slot;
         phase_mark(slot, 0);
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); tc::mbar_init(&conv_bar[i], 4); }
+        for (int i = 0; i < S; ++i) {
+            tc::mbar_init(&wfull_bar[i], 1); tc::mbar_init(&afull_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); tc::mbar_init(&conv_bar[i], 4);
+        }
         tc::mbar_init(tmem_full_bar, 1);
         tc::fence_mbar_init();
     }
@@ -121,10 +126,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
+            const bool presplit = !SWAP && p.presplit != 0;
+            const uint32_t w_tx = SWAP ? (uint32_t)kABytes : (uint32_t)(Cfg::kNBytes * (presplit ? 2 : 1));
+            const uint32_t a_tx = SWAP ? (uint32_t)Cfg::kNBytes : (uint32_t)kABytes;
             auto load_weights = [&](int it) {
                 const int s = it % S;
                 uint8_t* st = smem + s * Cfg::kStageBytes;
-                tc::tma_load_2d(SWAP ? st : st + kABytes, &p.tmB, &full_bar[s], (kb + it) * kBK, cout0);
+                tc::tma_load_2d(SWAP ? st : st + kABytes, &p.tmB, &wfull_bar[s], (kb + it) * kBK, cout0);
+                if (presplit) tc::tma_load_2d(st + kABytes + Cfg::kNBytes, &p.tmBlo, &wfull_bar[s], (kb + it) * kBK, cout0);
             };
             auto load_acts = [&](int it) {
                 const int s = it % S;
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                     ox = (ox - px) >> 1;
                 }
                 uint8_t* st = smem + s * Cfg::kStageBytes;
-                tc::tma_load_4d(SWAP ? st + kABytes : st, &p.tmA[map], &full_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
+                tc::tma_load_4d(SWAP ? st + kABytes : st, &p.tmA[map], &afull_bar[s], cc * kBK, w0 + ox, h0 + oy, n0);
             };
             // PDL: the weights do not depend on the previous kernel -- the first S stages of weight tiles stream in while it drains;
             // the activation tiles of those stages follow once griddepcontrol.wait returns.
@@ -147,18 +156,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             phase_mark(pslot, 1);
             pdl_trigger();
             for (int it = 0; it < pre; ++it) {
-                tc::mbar_expect_tx(&full_bar[it], kABytes + Cfg::kNBytes);
+                tc::mbar_expect_tx(&wfull_bar[it], w_tx);
                 load_weights(it);
             }
             pdl_wait();
             phase_mark(pslot, 2);
             trace_mark();
-            for (int it = 0; it < pre; ++it) load_acts(it);
+            for (int it = 0; it < pre; ++it) {
+                tc::mbar_expect_tx(&afull_bar[it], a_tx);
+                load_acts(it);
+            }
             for (int it = pre; it < niter; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 tc::mbar_wait(&empty_bar[s], ph ^ 1u);
-                tc::mbar_expect_tx(&full_bar[s], kABytes + Cfg::kNBytes);
+                tc::mbar_expect_tx(&afull_bar[s], a_tx);
+                tc::mbar_expect_tx(&wfull_bar[s], w_tx);
                 load_acts(it);
                 load_weights(it);
             }
@@ -203,35 +216,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             pix_s[et] = (n < p.NB && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        pdl_wait();   // residual reads / output writes below must see the previous kernel's results (bias is a constant)
 
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int it = 0; it < niter; ++it) {
+        uint64_t* mside_bar = SWAP ? wfull_bar : afull_bar;   // arrival of the 128-row tile (weights in swap mode)
+        uint64_t* nside_bar = SWAP ? afull_bar : wfull_bar;
+        // (1) M-side row r of stage s: 8 swizzled 16-byte chunks -> hi / lo -> TMEM columns [kABase + 64 s, +32) / [+32, +64)
+        auto convert_m = [&](int it) {
             const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            tc::mbar_wait(&full_bar[s], ph);
-            uint8_t* st = smem + s * Cfg::kStageBytes;
-            // (1) M-side row r: 8 swizzled 16-byte chunks -> hi / lo -> TMEM columns [kABase + 64 s, +32) / [+32, +64)
-            {
-                const uint8_t* rowp = st + r * 128;
-                uint32_t hi[32], lo[32];
+            tc::mbar_wait(&mside_bar[s], (uint32_t)(it / S) & 1u);
+            const uint8_t* rowp = smem + s * Cfg::kStageBytes + r * 128;
+            uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-                    const float f[4] = {v.x, v.y, v.z, v.w};
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+                const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-                        hi[c * 4 + e] = p.raw_hi ? __float_as_uint(f[e]) : h;
-                        lo[c * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+                    hi[c * 4 + e] = p.raw_hi ? __float_as_uint(f[e]) : h;
+                    lo[c * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
                 }
-                const uint32_t ta = lane_addr + (uint32_t)(Cfg::kABase + 64 * s);
-                tmem_st_32x32(ta, hi);
-                tmem_st_32x32(ta + 32, lo);
             }
-            // (2) N-side tile: hi in place, lo to the second buffer (same offsets => same swizzled layout)
-            {
+            const uint32_t ta = lane_addr + (uint32_t)(Cfg::kABase + 64 * s);
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32, lo);
+        };
+        // (2) N-side tile of stage s: hi in place, lo to the second buffer (same offsets => same swizzled layout); nothing to convert when the
+        //     weights arrive pre-split (hi and lo tiles are TMA-loaded straight into the two buffers).  Then hand the stage to the MMA issuer.
+        auto convert_n_and_release = [&](int it) {
+            const int s = it % S;
+            tc::mbar_wait(&nside_bar[s], (uint32_t)(it / S) & 1u);
+            if (SWAP || !p.presplit) {
+                uint8_t* st = smem + s * Cfg::kStageBytes;
                 float4* nraw = reinterpret_cast<float4*>(st + kABytes);
                 float4* nlo = reinterpret_cast<float4*>(st + kABytes + Cfg::kNBytes);
 #pragma unroll 2
@@ -251,10 +267,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&conv_bar[s]);
+        };
+        // Swap-AB: the 128-row tiles are WEIGHTS, which the producer streams in before the dependency wait -- convert all of the first ring's
+        // tiles into tensor memory up front, so that once the (small) activation tiles land only their split and the MMAs remain.
+        const int pre = SWAP ? (niter < S ? niter : S) : 0;
+        for (int it = 0; it < pre; ++it) convert_m(it);
+        for (int it = 0; it < pre; ++it) convert_n_and_release(it);
+        for (int it = pre; it < niter; ++it) {
+            convert_m(it);
+            convert_n_and_release(it);
         }
 
         // ---- epilogue
         const bool use_red = (p.splits > 1) || (p.accumulate != 0);
+        pdl_wait();   // residual reads / output writes below must see the previous kernel's results (returns at once: the activations are in)
         tc::mbar_wait(tmem_full_bar, 0);
         tc::fence_after_sync();
         if (et == 0) phase_mark(pslot, 5);
@@ -294,28 +320,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 }
             }
         } else {
-            // rows = output channels (this thread: cout0 + r), columns = the BN pixels of the tile
-            const int c = cout0 + r;
-            const bool cvalid = c < p.Cout;
-            const float bv = bias_s[r];
-            const bool add_res = (p.residual != nullptr && blockIdx.z == 0);
+            // rows = output channels (this thread: cout0 + r), columns = the BN pixels of the tile.  The accumulator is transposed through
+            // shared memory (the operand stages are idle by now) so that global traffic is 16-byte vectors along the channel dimension:
+            // one warp = the 128 channels of one pixel = 512 contiguous bytes per red.v4 / st.v4 instruction (scalar reds cost 3.7 us for 64 pixels).
+            constexpr int kLd = 132;                                    // floats per staged pixel row (16-byte aligned, bank-conflict free)
+            float* stg = reinterpret_cast<float*>(smem);
 #pragma unroll 1
             for (int j = 0; j < Cfg::kDCols / 32; ++j) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32(lane_addr + (uint32_t)(j * 32), v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int pj = j * 32 + e;                          // pixel index inside the tile (uniform across the warp)
-                    if (pj < BN) {
-                        const int pix = pix_s[pj];
-                        if (cvalid && pix >= 0) {
-                            float x = __uint_as_float(v[e]) + bv;
-                            if (add_res) x += __ldg(p.residual + (int64_t)pix * p.ldr + c);
-                            float* dst = p.out + (int64_t)pix * p.ldo + c;
-                            if (use_red) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(x) : "memory");
-                            else *dst = x;
-                        }
+                for (int e = 0; e < 32; ++e)
+                    if (j * 32 + e < BN) stg[(j * 32 + e) * kLd + r] = __uint_as_float(v[e]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool add_res = (p.residual != nullptr && blockIdx.z == 0);
+            for (int idx = et; idx < BN * 32; idx += 128) {
+                const int pj = idx >> 5, c4 = idx & 31;
+                const int pix = pix_s[pj];
+                const int c = cout0 + c4 * 4;
+                if (pix >= 0 && c < p.Cout) {
+                    float4 a = *reinterpret_cast<const float4*>(stg + pj * kLd + c4 * 4);
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
+                    a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                    if (add_res) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)pix * p.ldr + c));
+                        a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
+                    }
+                    float* dst = p.out + (int64_t)pix * p.ldo + c;
+                    if (use_red) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = a;
                     }
                 }
             }

@@ -156,8 +156,51 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     }
 }
 
+// Row-coalesced statistics: CTA (slab, n) walks whole pixel rows of its slab, thread t keeps ONE float4 column (so one group) per pass over
+// <= 256 columns and sums (sum, sumsq) in fp64; the per-thread sums meet in shared memory, one thread per group folds its columns and
+// writes the slab's partial.  Versus the group-major kernel above this reads every 32-byte sector once (with narrow groups -- the VAE's
+// GroupNorm(32) over 128 channels -- a group is 16 bytes of each pixel and the group-major CTAs pulled every sector twice).
+// Needs 4 | C/G, C/4 a divisor or a multiple of 256, and a group not wider than one pass.
+__global__ void __launch_bounds__(256) gn_stats_rows_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, int S,
+                                                           double2* __restrict__ partial) {
+    pdl_sync();
+    __shared__ double sh_s[256], sh_ss[256];
+    const int sl = blockIdx.x, n = blockIdx.y;
+    const int C4 = C >> 2, Cg4 = (C / G) >> 2;
+    const int cols = C4 < 256 ? C4 : 256, passes = C4 < 256 ? 1 : C4 / 256;
+    const int rpi = 256 / cols;                          // pixel rows per block iteration
+    const int p0 = (int)(((int64_t)HW * sl) / S), p1 = (int)(((int64_t)HW * (sl + 1)) / S);
+    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    const int gpp = cols / Cg4;                          // groups per pass
+    for (int pass = 0; pass < passes; ++pass) {
+        const float* base = x + (int64_t)n * HW * ldx + (pass * 256 + tc) * 4;
+        double s = 0.0, ss = 0.0;
+        for (int p = p0 + tr; p < p1; p += rpi) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * ldx));
+            s += (double)(v.x + v.y + v.z + v.w);
+            ss += (double)(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+        }
+        sh_s[threadIdx.x] = s;
+        sh_ss[threadIdx.x] = ss;
+        __syncthreads();
+        if (threadIdx.x < gpp) {
+            double ts = 0.0, tss = 0.0;
+            for (int r = 0; r < rpi; ++r)
+                for (int j = 0; j < Cg4; ++j) {
+                    const int i = r * cols + threadIdx.x * Cg4 + j;
+                    ts += sh_s[i];
+                    tss += sh_ss[i];
+                }
+            const int g = pass * gpp + threadIdx.x;
+            partial[((int64_t)n * G + g) * S + sl] = make_double2(ts, tss);
+        }
+        __syncthreads();
+    }
+}
+
 // y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ), rounded to tf32.  film [NB, 2C] (scale | shift) or null.  grid (blocks, NB)
 constexpr int kGnMaxGroups = 32;
+constexpr int kGnMaxSlabs = 256;   // partials per (image, group): sizes the workspace (sfb_groupnorm_ws_floats)
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int64_t ldx, const double2* __restrict__ partial, int S, float eps,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
@@ -566,6 +609,52 @@ __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v
     }
 }
 
+// GlobalContext tail fused: gate[n][c] = sigmoid(b2[c] + W2[c][:] . hid[n][:]) (Conv2d(hidden, dim_out, 1) + Sigmoid, imagen_pytorch.py:929-933)
+// and out = h * gate + res (ResnetBlock tail, :727-729) in one launch.  grid (C / 8, NB): a CTA owns 8 channels of one image -- each warp
+// evaluates one gate channel (a 2 KB weight row), then all threads stream the CTA's 32-byte channel slab of every pixel.
+__global__ void __launch_bounds__(256) gate_mlp_residual_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ hid,
+                                                               const float* __restrict__ W2, const float* __restrict__ b2, int Hd,
+                                                               const float* __restrict__ res, int64_t ldr, float* __restrict__ out, int64_t ldo, int HW,
+                                                               int C) {
+    pdl_sync();
+    __shared__ __align__(16) float gate_s[8];
+    const int n = blockIdx.y, c0 = blockIdx.x * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const int c = c0 + warp;
+        float acc = 0.f;
+        if (c < C) {
+            const float* wr = W2 + (int64_t)c * Hd;
+            const float* hr = hid + (int64_t)n * Hd;
+            if ((Hd & 3) == 0) {
+                for (int k = lane * 4; k < Hd; k += 128) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(hr + k));
+                    acc += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+                }
+            } else {
+                for (int k = lane; k < Hd; k += 32) acc += __ldg(wr + k) * __ldg(hr + k);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) gate_s[warp] = (c < C) ? sigmoid_f(acc + b2[c]) : 0.f;
+    }
+    __syncthreads();
+    const int q = threadIdx.x & 1, pg = threadIdx.x >> 1;
+    const int c = c0 + q * 4;
+    if (c >= C) return;
+    const float4 g = *reinterpret_cast<const float4*>(gate_s + q * 4);
+    const float* hb = h + (int64_t)n * HW * ldh + c;
+    const float* rb = res + (int64_t)n * HW * ldr + c;
+    float* ob = out + (int64_t)n * HW * ldo + c;
+#pragma unroll 4
+    for (int p = pg; p < HW; p += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(hb + (int64_t)p * ldh));
+        const float4 r = __ldg(reinterpret_cast<const float4*>(rb + (int64_t)p * ldr));
+        *reinterpret_cast<float4*>(ob + (int64_t)p * ldo) = make_float4(v.x * g.x + r.x, v.y * g.y + r.y, v.z * g.z + r.z, v.w * g.w + r.w);
+    }
+}
+
 // ------------------------------------------------------------------------------------ VAE helpers (ldm AttnBlock / Upsample)
 // y[r][:] = softmax(scale * x[r][:]) over `cols` columns; one CTA per row (ldm model.py:183-190: single-head attention over h*w tokens)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int cols,
@@ -655,7 +744,7 @@ int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W
     return check_launch("pixel_shuffle_silu");
 }
 
-int sfb_groupnorm_ws_floats(int NB, int G) { return ((2 * NB * G + 3) / 4) * 4 + NB * G * 64 * 4; }
+int sfb_groupnorm_ws_floats(int NB, int G) { return ((2 * NB * G + 3) / 4) * 4 + NB * G * kGnMaxSlabs * 4; }
 
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
                        int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy, void* stream) {
@@ -665,11 +754,23 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     cudaStream_t st = as_stream(stream);
     // workspace: 16-byte aligned fp64 partials [NB*G*S][2] (the leading (mean, rstd) slots of the old layout stay unused)
     SFB_REQUIRE(G <= kGnMaxGroups, "groupnorm_nhwc: at most 32 groups");
-    int S = 1;
-    while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
     (void)counters;
-    SFB_LAUNCH(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, S, partial);
+    const int C4 = C / 4, Cg = C / G;
+    const bool rows_ok = (Cg % 4 == 0) && (C4 <= 256 ? (256 % C4 == 0) : (C4 % 256 == 0)) && (Cg / 4 <= (C4 < 256 ? C4 : 256));
+    int S = 1;
+    if (rows_ok) {
+        const int rpi = 256 / (C4 < 256 ? C4 : 256);
+        const int want = (2 * sm_count() + NB - 1) / NB;                // ~2 CTAs per SM over the batch
+        S = HW / (rpi * 2);                                             // at least two block iterations per slab
+        if (S > want) S = want;
+        if (S > kGnMaxSlabs) S = kGnMaxSlabs;
+        if (S < 1) S = 1;
+        SFB_LAUNCH(gn_stats_rows_kernel, dim3(S, NB), 256, 0, st, x, ldx, HW, C, G, S, partial);
+    } else {
+        while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
+        SFB_LAUNCH(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, S, partial);
+    }
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t img4 = (int64_t)HW * (C / 4);
     int ab = (int)((img4 + 256 * 4 - 1) / (256 * 4));     // ~4 float4 per thread
@@ -756,6 +857,15 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     SFB_REQUIRE(sm <= 48 * 1024, "gca_pool: image too large for the single-pass pooling kernel");
     SFB_LAUNCH(gca_pool_kernel, dim3(ceil_div(C, kGcaCols), NB), 256, sm, st, x, ldx, logits_ws, pooled, HW, C);
     return check_launch("gca_pool(pool)");
+}
+
+int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, const float* w2, const float* b2, int Hd, const float* res, int64_t ldr,
+                               float* out, int64_t ldo, int NB, int HW, int C, void* stream) {
+    SFB_REQUIRE(h && hid && w2 && b2 && res && out, "gate_mlp_residual: null pointer");
+    SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && Hd > 0, "gate_mlp_residual: channel counts must be multiples of 4");
+    if (NB == 0 || HW == 0) return SFB_OK;
+    SFB_LAUNCH(gate_mlp_residual_kernel, dim3(ceil_div(C, 8), NB), 256, 0, as_stream(stream), h, ldh, hid, w2, b2, Hd, res, ldr, out, ldo, HW, C);
+    return check_launch("gate_mlp_residual");
 }
 
 int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream) {

@@ -369,15 +369,27 @@ class Unet(nn.Module):
         for b in film_names:
             film_off[b] = (o, P[f'{b}.time_mlp.1.weight'].shape[0])
             o += P[f'{b}.time_mlp.1.weight'].shape[0]
-        self._plan = dict(P=P, packed=packed, film_w=film_w, film_b=film_b, film_off=film_off)
+        self._plan = dict(P=P, packed=packed, split={}, film_w=film_w, film_b=film_b, film_off=film_off)
         return self
 
     # ------------------------------------------------------------------------------------------ forward pieces (NHWC)
+    def _split(self, key, x_pixels):
+        """pre-split (hi, lo) copy of a packed weight for launches that run the tensor-bound (non swap-AB) kernel: more than 64 output pixels in
+        3xTF32 mode.  Made on first use; the weight-streaming layers of a batch-1 evaluation never get one."""
+        pl = self._plan
+        if x_pixels <= 64 or ops.get_precision() != 'tf32x3':
+            return None
+        sp = pl['split'].get(key)
+        if sp is None:
+            sp = pl['split'][key] = ops.split_packed_weight(pl['packed'][key])
+        return sp
+
     def _conv(self, name, x, k, stride=1, pad=0, residual=None, out=None, accumulate=False):
         pl = self._plan
         w = pl['packed'][name + '.weight']
+        npix = x.shape[0] * (x.shape[1] // stride) * (x.shape[2] // stride)
         return ops.conv2d_nhwc(x, w, w.shape[0], k, k, stride, pad, bias=pl['P'].get(name + '.bias'), residual=residual, out=out,
-                               accumulate=accumulate)
+                               accumulate=accumulate, w_split=self._split(name + '.weight', npix))
 
     def _linear_rows(self, name, x, bias=True, round_out=False):
         """token projection [.., K] -> [.., O]: fp32 GEMV for a handful of rows, tensor cores (swap-AB tile: the rows are the N side) from 16 rows up --
@@ -388,7 +400,7 @@ class Unet(nn.Module):
         rows = x.numel() // x.shape[-1]
         if rows < 16 or (name + '.weight') not in pl['packed']:
             return ops.linear_small(x, w.reshape(w.shape[0], -1), b, round_to_tf32=round_out)
-        return ops.linear_tc(x, pl['packed'][name + '.weight'], w.shape[0], bias=b)
+        return ops.linear_tc(x, pl['packed'][name + '.weight'], w.shape[0], bias=b, w_split=self._split(name + '.weight', rows))
 
     def _resnet(self, pfx, x, film_all, c_tokens, taps=None):
         pl = self._plan
@@ -407,8 +419,7 @@ class Unet(nn.Module):
             pooled = ops.gca_pool(h2, P[f'{pfx}.gca.to_k.weight'], P[f'{pfx}.gca.to_k.bias'])
             w0, w2 = P[f'{pfx}.gca.net.0.weight'], P[f'{pfx}.gca.net.2.weight']
             hid = ops.linear_small(pooled, w0.reshape(w0.shape[0], -1), P[f'{pfx}.gca.net.0.bias'], post=1)
-            gate = ops.linear_small(hid, w2.reshape(w2.shape[0], -1), P[f'{pfx}.gca.net.2.bias'], post=2)
-            out = ops.gate_residual(h2, gate, res)
+            out = ops.gate_mlp_residual(h2, hid, w2.reshape(w2.shape[0], -1), P[f'{pfx}.gca.net.2.bias'], res)   # gate GEMV + sigmoid + h*gate + res
         else:
             out = self._conv(f'{pfx}.block2.project', a2, 3, 1, 1, residual=res)
         if taps is not None:
@@ -474,7 +485,8 @@ class Unet(nn.Module):
             o = 0
             for i, k in enumerate(self.kernel_sizes):
                 w = pl['packed'][f'init_conv.convs.{i}.weight@cond']
-                ops.conv2d_nhwc(cn, w, w.shape[0], k, k, 1, (k - 1) // 2, bias=pl['P'].get(f'init_conv.convs.{i}.bias'), out=h0[..., o:o + w.shape[0]])
+                ops.conv2d_nhwc(cn, w, w.shape[0], k, k, 1, (k - 1) // 2, bias=pl['P'].get(f'init_conv.convs.{i}.bias'), out=h0[..., o:o + w.shape[0]],
+                                w_split=self._split(f'init_conv.convs.{i}.weight@cond', nb * hh * ww))
                 o += w.shape[0]
         return h0
 
@@ -516,7 +528,8 @@ class Unet(nn.Module):
             o = 0
             for i, k in enumerate(self.kernel_sizes):
                 w = pl['packed'][f'init_conv.convs.{i}.weight@x']
-                ops.conv2d_nhwc(x4, w, w.shape[0], k, k, 1, (k - 1) // 2, out=h0[..., o:o + w.shape[0]], accumulate=True)
+                ops.conv2d_nhwc(x4, w, w.shape[0], k, k, 1, (k - 1) // 2, out=h0[..., o:o + w.shape[0]], accumulate=True,
+                                w_split=self._split(f'init_conv.convs.{i}.weight@x', nb * hh * ww))
                 o += w.shape[0]
         else:
             # cat(cond_images * keep_mask, x) -> NHWC (imagen_pytorch.py:1496-1504); prob 0 keeps, prob 1 drops everything

@@ -190,7 +190,7 @@ class _Sm100Engine:
         P = {n: p.detach() for n, p in vae.named_parameters()}
         if next(iter(P.values())).device.type != 'cuda':
             raise RuntimeError('the sm_100a VAE engine needs CUDA parameters')
-        self.P, self.W, self.B = P, {}, {}
+        self.P, self.W, self.B, self.S = P, {}, {}, {}
         for n, p in P.items():
             if n.endswith('.weight') and p.dim() == 4:
                 base = n[:-len('.weight')]
@@ -200,13 +200,14 @@ class _Sm100Engine:
                     w = torch.cat((w, w.new_zeros(padc, *w.shape[1:])), dim=0)
                     b = torch.cat((b, b.new_zeros(padc))) if b is not None else None
                 self.W[base] = ops.pack_conv_weight(w)
+                self.S[base] = ops.split_packed_weight(self.W[base]) if ops.get_precision() == 'tf32x3' else None   # these convolutions are tensor-bound
                 self.B[base] = None if b is None else b.float().contiguous()
 
     # ---- building blocks
     def conv(self, name, x, k, stride=1, pad=None, pad_after=None, residual=None):
         w = self.W[name]
         pad = (k - 1) // 2 if pad is None else pad
-        return self.ops.conv2d_nhwc(x, w, w.shape[0], k, k, stride, pad, bias=self.B[name], residual=residual, pad_after=pad_after)
+        return self.ops.conv2d_nhwc(x, w, w.shape[0], k, k, stride, pad, bias=self.B[name], residual=residual, pad_after=pad_after, w_split=self.S[name])
 
     def gn(self, name, x, swish):
         return self.ops.groupnorm(x, self.GROUPS, self.P[name + '.weight'], self.P[name + '.bias'], None, swish, eps=self.EPS)
@@ -228,13 +229,14 @@ class _Sm100Engine:
         wv = self.P[pfx + '.v.weight'].reshape(c, c)
         for b in range(nb):
             rows = hn[b].reshape(n, c)
-            q = ops.linear_tc(rows, self.W[pfx + '.q'], c, bias=self.B[pfx + '.q'])
-            k = ops.linear_tc(rows, self.W[pfx + '.k'], c, bias=self.B[pfx + '.k'])
+            q = ops.linear_tc(rows, self.W[pfx + '.q'], c, bias=self.B[pfx + '.q'], w_split=self.S[pfx + '.q'])
+            k = ops.linear_tc(rows, self.W[pfx + '.k'], c, bias=self.B[pfx + '.k'], w_split=self.S[pfx + '.k'])
             scores = ops.linear_tc(q, k, n)                           # q k^T: the keys are the GEMM's [Cout = n][K = c] operand
             probs = ops.softmax_rows(scores, scale=float(c) ** -0.5)
             vt = ops.linear_tc(wv, rows, n)                           # (W_v h^T) = v^T without bias: [c][n], the K-major operand of P.V
             o = ops.linear_tc(probs, vt, c, bias=self.B[pfx + '.v'])   # rows of P sum to 1, so v's bias is added once per output row
-            ops.linear_tc(o, self.W[pfx + '.proj_out'], c, bias=self.B[pfx + '.proj_out'], residual=x[b].reshape(n, c), out=out[b].reshape(n, c))
+            ops.linear_tc(o, self.W[pfx + '.proj_out'], c, bias=self.B[pfx + '.proj_out'], residual=x[b].reshape(n, c), out=out[b].reshape(n, c),
+                          w_split=self.S[pfx + '.proj_out'])
         return out
 
     # ---- Encoder.forward (model.py:368-460) + quant_conv (autoencoder.py:311-315)

@@ -63,6 +63,13 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return (round_tf32(p) if get_precision() == 'tf32' else p).contiguous()
 
 
+def split_packed_weight(wp: torch.Tensor) -> torch.Tensor:
+    """[2, Cout, K]: hi = the TF32 part the tensor core uses (bits & 0xFFFFE000), lo = w - hi (exact in fp32).  The tensor-bound convolutions
+    of the 3xTF32 engine TMA-load both tiles instead of splitting the weight tile in shared memory on every k-step."""
+    hi = (wp.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return torch.stack((hi, wp - hi), dim=0).contiguous()
+
+
 def _nhwc_meta(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
     """(NB, H, W, C, ld) of an NHWC tensor or channel-slice view of one"""
     assert t.dim() == 4 and t.is_cuda and t.dtype == torch.float32, 'expected a CUDA fp32 NHWC tensor'
@@ -146,7 +153,8 @@ def _conv_out(shape, device):
 
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                accumulate: bool = False, splits: int = 0, bn: int = 0, pad_after: Optional[int] = None) -> torch.Tensor:
+                accumulate: bool = False, splits: int = 0, bn: int = 0, pad_after: Optional[int] = None,
+                w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, h, w, cin, ldx = _nhwc_meta(x)
     if pad_after is None:
         pad_after = pad
@@ -162,13 +170,15 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw:
     if residual is not None:
         rnb, rh, rw, rc, ldr = _nhwc_meta(residual)
         assert (rnb, rh, rw, rc) == (nb, ho, wo, cout)
-    lib.call('sfb_conv2d_nhwc_tf32_pad', x.data_ptr(), nb, h, w, cin, ldx,
-             lib.fptr(w_packed, 'w_packed'), cout, kh, kw, stride, pad, pad_after, lib.fptr(bias, 'bias'),
+    if w_split is not None:
+        assert w_split.shape == (2,) + tuple(w_packed.shape)
+    lib.call('sfb_conv2d_nhwc_tf32_ex', x.data_ptr(), nb, h, w, cin, ldx,
+             lib.fptr(w_packed, 'w_packed'), lib.fptr(w_split, 'w_split'), cout, kh, kw, stride, pad, pad_after, lib.fptr(bias, 'bias'),
              None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
     return out
 
 
-def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=None, residual=None, out=None) -> torch.Tensor:
+def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=None, residual=None, out=None, w_split=None) -> torch.Tensor:
     """nn.Linear on the tensor cores: rows [T, K] are treated as T 1x1 'images'"""
     t, k, ld = _rows_meta(x)
     x4 = x.as_strided((t, 1, 1, k), (ld, ld, ld, 1))
@@ -181,7 +191,19 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=N
     if residual is not None:
         tr, cr, ldr = _rows_meta(residual)
         r4 = residual.as_strided((t, 1, 1, out_features), (ldr, ldr, ldr, 1))
-    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed)
+    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed, w_split=w_split)
+    return out
+
+
+def gate_mlp_residual(h: torch.Tensor, hid: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, res: torch.Tensor) -> torch.Tensor:
+    """out = h * sigmoid(hid @ w2.T + b2)[:, None, None, :] + res   (GlobalContext's last layer + the ResnetBlock tail in one launch)"""
+    nb, hh, ww, c, ldh = _nhwc_meta(h)
+    _, _, _, _, ldr = _nhwc_meta(res)
+    out = torch.empty(nb, hh, ww, c, dtype=torch.float32, device=h.device)
+    hd = hid.shape[-1]
+    assert tuple(w2.shape) == (c, hd) and hid.numel() == nb * hd
+    lib.call('sfb_gate_mlp_residual_nhwc', h.data_ptr(), ldh, lib.fptr(hid), lib.fptr(w2), lib.fptr(b2), hd, res.data_ptr(), ldr, out.data_ptr(), c,
+             nb, hh * ww, c, lib.stream())
     return out
 
 

@@ -80,3 +80,24 @@ def test_tensor_core_reads_tf32_by_truncation():
         rel = ((out[3] - out[2]).norm() / out[2].norm()).item()
         print(f'raw-hi vs masked-hi {(nb, h, w, cin, cout, k)}: bit-identical={same[-1]} rel diff {rel:.3e}')
     print('TENSOR CORE TF32 READ IS A TRUNCATION' if all(same) else 'tensor core tf32 read is NOT a plain truncation')
+
+
+@pytest.mark.parametrize('case', [(1, 32, 32, 256, 256, 3, 1, 1), (2, 16, 16, 96, 160, 3, 1, 1), (1, 64, 64, 128, 128, 3, 2, 1), (300, 1, 1, 512, 384, 1, 1, 0)])
+def test_presplit_weights_match_in_kernel_split(case):
+    """(hi, lo) copies of the weights loaded by TMA vs the same split done by the converter warps: the operands of every MMA are
+    bit-identical, so the results must be (for equal split-K factors)."""
+    from sparsefusion_b200 import ops
+    nb, h, w, cin, cout, k, stride, pad = case
+    ops.set_precision('tf32x3')
+    g = torch.Generator(device='cuda').manual_seed(9 + cin)
+    x = torch.randn(nb, h, w, cin, device='cuda', generator=g)
+    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device='cuda', generator=g)
+    wp = ops.pack_conv_weight(wt)
+    sp = ops.split_packed_weight(wp)
+    assert torch.equal(sp[0] + sp[1], wp) and ((sp[0].view(torch.int32) & 0x1FFF) == 0).all()
+    y0 = ops.conv2d_nhwc(x, wp, cout, k, k, stride, pad, bias=b, splits=1)
+    y1 = ops.conv2d_nhwc(x, wp, cout, k, k, stride, pad, bias=b, splits=1, w_split=sp)
+    assert torch.equal(y0, y1)
+    ref = _ref(x, wt, b, stride, pad)
+    assert ((y1 - ref).norm() / ref.norm()).item() < 2e-5

@@ -37,7 +37,7 @@ def test_pixel_shuffle_silu():
 
 
 @pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
-                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4)])
+                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32)])
 @pytest.mark.parametrize('film', [False, True])
 def test_groupnorm_film_silu(shape, film):
     from sparsefusion_b200 import ops
@@ -145,3 +145,17 @@ def test_gca_pool_and_gate_residual(shape):
     res = torch.randn(nb, h, w, c, device='cuda')
     _close(ops.gate_residual(x, gate, res), x * gate[:, None, None, :] + res, 1e-6, 1e-6)
     _close(ops.gate_residual(x, None, res), x + res, 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize('shape', [(1, 32, 32, 256), (2, 4, 4, 1024), (3, 5, 3, 36)])
+def test_gate_mlp_residual(shape):
+    from sparsefusion_b200 import ops
+    nb, h, w, c = shape
+    hd = max(3, c // 2)
+    x = torch.randn(nb, h, w, c, device='cuda')
+    res = torch.randn(nb, h, w, c, device='cuda')
+    hid = torch.randn(nb, hd, device='cuda')
+    w2, b2 = torch.randn(c, hd, device='cuda') / hd ** 0.5, torch.randn(c, device='cuda')
+    gate = torch.sigmoid(hid.double() @ w2.double().T + b2.double())
+    ref = (x.double() * gate[:, None, None, :] + res.double()).float()
+    _close(ops.gate_mlp_residual(x, hid, w2, b2, res), ref, 2e-6, 2e-6)
