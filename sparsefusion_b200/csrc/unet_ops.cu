@@ -762,7 +762,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     if (rows_ok) {
         const int rpi = 256 / (C4 < 256 ? C4 : 256);
         const int want = (2 * sm_count() + NB - 1) / NB;                // ~2 CTAs per SM over the batch
-        S = HW / (rpi * 2);                                             // at least two block iterations per slab
+        S = HW / (rpi * 8);                                             // at least eight block iterations per slab (few, fat partials: the apply kernel folds them)
         if (S > want) S = want;
         if (S > kGnMaxSlabs) S = kGnMaxSlabs;
         if (S < 1) S = 1;

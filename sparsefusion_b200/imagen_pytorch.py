@@ -490,6 +490,33 @@ class Unet(nn.Module):
                 o += w.shape[0]
         return h0
 
+    @torch.no_grad()
+    def precompute_time(self, time: torch.Tensor) -> dict:
+        """everything of an evaluation that depends on the noise level only (imagen_pytorch.py:1517-1522, :1600-1604 and every block's time MLP,
+        :698-704): rows of ``t`` [T, time_cond_dim], ``c`` [T, tokens, cond_dim] and ``film`` [T, sum 2*dim_out] for T log-SNR values.  A PLMS run knows
+        its n+1 noise levels up front: evaluating them in one batch reads the 143 MB of time-MLP weights once per run instead of once per UNet
+        evaluation, and takes six launches (66 us) off the critical path of every evaluation.  Pass row i as ``forward(time_features=...)``."""
+        if self._plan is None:
+            self.prepare()
+        pl = self._plan
+        P = pl['P']
+        time = time.float().contiguous()
+        rows = time.shape[0]
+        with torch.cuda.device(time.device):
+            four = ops.time_fourier(time, P['to_time_hiddens.0.weights'])
+            th = ops.linear_small(four, P['to_time_hiddens.1.weight'], P['to_time_hiddens.1.bias'], post=1)
+            tokens = ops.linear_small(th, P['to_time_tokens.0.weight'], P['to_time_tokens.0.bias']).view(rows, self.num_time_tokens, self.cond_dim)
+            t = ops.linear_small(th, P['to_time_cond.0.weight'], P['to_time_cond.0.bias'])
+            c = ops.layernorm(tokens, P['norm_cond.weight'], P['norm_cond.bias'], round_to_tf32=False)
+            if rows >= 16:      # many noise levels at once: one pass over the fused time-MLP weights on the tensor cores (swap-AB tile)
+                if 'film_w' not in pl['packed']:
+                    pl['packed']['film_w'] = ops.pack_conv_weight(pl['film_w'])
+                film_all = ops.linear_tc(torch.nn.functional.silu(t), pl['packed']['film_w'], pl['film_w'].shape[0], bias=pl['film_b'],
+                                         w_split=self._split('film_w', rows))
+            else:
+                film_all = ops.linear_small(t, pl['film_w'], pl['film_b'], pre=1)  # every block's SiLU->Linear time MLP at once
+        return dict(t=t, c=c, film=film_all)
+
     def forward_with_cond_scale(self, *args, cond_scale=1., **kwargs):
         logits = self.forward(*args, **kwargs)
         if cond_scale == 1:
@@ -499,7 +526,8 @@ class Unet(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, conditional_embeds=None, conditional_mask=None,
-                cond_images=None, cond_drop_prob=0., taps: Optional[dict] = None, cond_features: Optional[torch.Tensor] = None):
+                cond_images=None, cond_drop_prob=0., taps: Optional[dict] = None, cond_features: Optional[torch.Tensor] = None,
+                time_features: Optional[dict] = None):
         if exists(lowres_cond_img) or exists(conditional_embeds):
             raise NotImplementedError('sparsefusion_b200.Unet: low-res / text conditioning are not part of the SparseFusion VLDM path')
         assert not (self.has_cond_image ^ (exists(cond_images) or exists(cond_features))), 'cond_images must be given iff the unet was built with cond_images_channels'
@@ -512,12 +540,12 @@ class Unet(nn.Module):
         need = self._arena_floats.get((nb, hh, ww)) if self.use_arena else None
         arena = ops.ArenaMeter() if (need is None and self.use_arena) else (ops.ZeroArena(need, dev) if need is not None else None)
         with torch.cuda.device(dev), ops.use_arena(arena):
-            y = self._forward_nhwc(x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev, cond_features)
+            y = self._forward_nhwc(x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev, cond_features, time_features)
         if isinstance(arena, ops.ArenaMeter):
             self._arena_floats[(nb, hh, ww)] = arena.floats
         return y
 
-    def _forward_nhwc(self, x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev, cond_features=None):
+    def _forward_nhwc(self, x, time, cond_images, cond_drop_prob, taps, P, nb, hh, ww, dev, cond_features=None, time_features=None):
         pl = self._plan
         if cond_features is not None:
             # init_conv = cached conv(W[:, :Cc], cond_images) (+ bias) + conv(W[:, Cc:], x): only the 4-channel term is evaluated here
@@ -555,13 +583,11 @@ class Unet(nn.Module):
         xcur = h0
         if taps is not None:
             taps['init_conv'] = xcur
-        # time conditioning (:1517-1522, :1600-1604), fp32 GEMVs
-        four = ops.time_fourier(time.float().contiguous(), P['to_time_hiddens.0.weights'])
-        th = ops.linear_small(four, P['to_time_hiddens.1.weight'], P['to_time_hiddens.1.bias'], post=1)
-        tokens = ops.linear_small(th, P['to_time_tokens.0.weight'], P['to_time_tokens.0.bias']).view(nb, self.num_time_tokens, self.cond_dim)
-        t = ops.linear_small(th, P['to_time_cond.0.weight'], P['to_time_cond.0.bias'])
-        c = ops.layernorm(tokens, P['norm_cond.weight'], P['norm_cond.bias'], round_to_tf32=False)
-        film_all = ops.linear_small(t, self._plan['film_w'], self._plan['film_b'], pre=1)  # every block's SiLU->Linear time MLP at once
+        # time conditioning (:1517-1522, :1600-1604): depends on `time` only -- evaluated here, or ahead of time for a whole sampling run
+        if time_features is None:
+            time_features = self.precompute_time(time)
+        t, c, film_all = time_features['t'], time_features['c'], time_features['film']
+        assert film_all.shape[0] == nb and c.shape[0] == nb, 'time_features rows must match the batch'
         if taps is not None:
             taps['t'], taps['c'] = t, c
 
@@ -623,12 +649,17 @@ class UnetGraph:
         self.timing = None   # set to [] to collect (start, stop) CUDA event pairs around every replay (bench.py)
 
     @torch.no_grad()
-    def __call__(self, x, time, cond_images, new_cond: bool = True):
+    def __call__(self, x, time, cond_images, new_cond: bool = True, time_features: Optional[dict] = None):
+        """``time_features`` = the rows of ``Unet.precompute_time`` for this batch (the PLMS sampler computes them for all its noise levels in one
+        batch); when absent they are evaluated here from ``time``, outside the graph."""
         key = (tuple(x.shape), tuple(cond_images.shape), x.device.index)
         g = self._graphs.get(key)
         launches = lambda: int(ops.lib.load().sfb_launch_count())
+        if time_features is None:
+            time_features = self.unet.precompute_time(time)
         if g is None:
-            sx, st, sc = x.clone(), time.clone().float(), cond_images.clone()
+            sx, sc = x.clone(), cond_images.clone()
+            sf = {k: v.clone() for k, v in time_features.items()}
             if self.unet._plan is None:
                 self.unet.prepare()
             side = torch.cuda.Stream(device=x.device)
@@ -636,7 +667,7 @@ class UnetGraph:
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture: lazy attribute setting, tensor-map cache, allocator, arena size
                     feat = self.unet.precompute_cond(sc)
-                    self.unet.forward(sx, st, cond_features=feat)
+                    self.unet.forward(sx, None, cond_features=feat, time_features=sf)
             torch.cuda.current_stream().wait_stream(side)
             cond_graph, graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             n0 = launches()
@@ -644,12 +675,14 @@ class UnetGraph:
                 feat = self.unet.precompute_cond(sc)
             n1 = launches()
             with torch.cuda.graph(graph):
-                out = self.unet.forward(sx, st, cond_features=feat)
-            g = self._graphs[key] = (graph, cond_graph, sx, st, sc, out, launches() - n1, n1 - n0, feat)
+                out = self.unet.forward(sx, None, cond_features=feat, time_features=sf)
+            g = self._graphs[key] = (graph, cond_graph, sx, sf, sc, out, launches() - n1, n1 - n0, feat)
             new_cond = True
-        graph, cond_graph, sx, st, sc, out, n_kernels, n_cond_kernels, _ = g
+        graph, cond_graph, sx, sf, sc, out, n_kernels, n_cond_kernels, _ = g
         sx.copy_(x)
-        st.copy_(time)
+        for k, v in sf.items():
+            if v.data_ptr() != time_features[k].data_ptr():
+                v.copy_(time_features[k])
         if new_cond:
             if sc.data_ptr() != cond_images.data_ptr():
                 sc.copy_(cond_images)

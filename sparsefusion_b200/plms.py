@@ -53,13 +53,13 @@ class PLMSSampler:
         self._graph = None
         self.last_unet_calls = 0
 
-    def _eps(self, unet, x, log_snr, cond_images, cond_scale):
+    def _eps(self, unet, x, log_snr, cond_images, cond_scale, time_features=None):
         self.last_unet_calls += 1
         if self.use_cuda_graph and cond_scale == 1:
             if self._graph is None or self._graph.unet is not unet:
                 self._graph = UnetGraph(unet)
             # cond_images is fixed for the whole sampling run: its share of init_conv is evaluated by the first call only
-            return self._graph(x, log_snr, cond_images, new_cond=(self.last_unet_calls == 1)).clone()
+            return self._graph(x, log_snr, cond_images, new_cond=(self.last_unet_calls == 1), time_features=time_features).clone()
         return unet.forward_with_cond_scale(x, log_snr, cond_images=cond_images, cond_scale=cond_scale)
 
     @torch.no_grad()
@@ -132,9 +132,20 @@ class PLMSSampler:
         n = img.numel()
         st = lib.stream
 
+        # the run's noise levels are known now: everything of the UNet that depends on them only (time embedding, conditioning tokens, all
+        # time MLPs) is evaluated for the whole run in one batch (Unet.precompute_time) instead of once per evaluation
+        tf_all = None
+        if self.use_cuda_graph and cond_scale == 1 and len(lin) > 1 and hasattr(unet, 'precompute_time'):
+            tf_all = unet.precompute_time(torch.tensor([_log_snr(t) for t in lin], dtype=torch.float32, device=img.device))
+        level = {t: i for i, t in enumerate(lin)}
+
         def eps_at(x, t):
             ls = torch.full((b,), _log_snr(t), dtype=torch.float32, device=x.device)
-            return self._eps(unet, x, ls, cond_images, cond_scale)
+            tf = None
+            if tf_all is not None:
+                i = level[t]
+                tf = {k: v[i:i + 1].expand(b, *v.shape[1:]) for k, v in tf_all.items()}
+            return self._eps(unet, x, ls, cond_images, cond_scale, time_features=tf)
 
         def update(x, eps_list, coefs, z, t, t_next):
             alpha, sigma, alpha_next, c, noise_scale = _step_scalars(t, t_next)

