@@ -164,16 +164,6 @@ int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int6
 int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH,
                             int KW, int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                             int accumulate, int splits, int bn, void* stream);
-/* GroupNorm + FiLM + SiLU folded into the convolution that consumes it (Block: norm -> scale/shift -> SiLU -> project, imagen_pytorch.py:640-656):
- * x is the RAW block input; the kernel's operand converter applies y = silu(a[c] x + b[c]) with (a, b) built per CTA from the fp64 statistics
- * partials of sfb_groupnorm_stats_nhwc (gn_slabs = sfb_groupnorm_slabs of the same shape), gamma / beta and the optional FiLM row
- * film = (scale[Cin] | shift[Cin]); zero padding stays zero.  One launch instead of GroupNorm-apply + convolution.
- * Supported (sfb_conv2d_gn_supported): 3xTF32 mode, NB == 1, stride 1, Cin % 32 == 0, Cin <= 2048, <= 32 groups. */
-int sfb_conv2d_gn_supported(int NB, int Cin, int G, int stride);
-int sfb_conv2d_gn_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* gn_partial, int gn_slabs, int groups, float eps,
-                            const float* gamma, const float* beta, const float* film, const float* w_packed, const float* w_hi_lo, int Cout, int KH,
-                            int KW, int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate, int splits,
-                            void* stream);
 int sfb_conv_weight_k(int Cin, int KH, int KW);
 /* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
 int sfb_conv_prof_enable(int on);
@@ -199,10 +189,6 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
                        int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy,
                        void* stream);
 int sfb_groupnorm_ws_floats(int NB, int G);
-/* statistics pass alone: `partial` receives NB*G*S fp64 (sum, sumsq) pairs, S = sfb_groupnorm_slabs(NB, HW, C, G) (<= 256), laid out
- * [(n*G + g)*S + slab]; 16-byte aligned, 4*NB*G*S floats.  Consumed by sfb_conv2d_gn_nhwc_tf32. */
-int sfb_groupnorm_slabs(int NB, int HW, int C, int G);
-int sfb_groupnorm_stats_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, float* partial, void* stream);
 /* LayerNorm / ChanLayerNorm (:301-329; gain g, optional bias b for nn.LayerNorm) over the last dim of [T,C] rows,
  * optionally of GELU(x) (ChanFeedForward :958-959), optionally + res (the `attn(x) + x` of :986) */
 int sfb_layernorm_rows(const float* x, int64_t ldx, const float* g, const float* b, const float* res, int64_t ldr, float* y, int64_t ldy, int T,

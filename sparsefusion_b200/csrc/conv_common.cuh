@@ -27,13 +27,6 @@ struct alignas(64) ConvGemmParams {
     int32_t KH, KW, pad, stride;
     int32_t k_iters, splits;
     int32_t accumulate;
-    // fused GroupNorm + FiLM + SiLU on the activation operand (v2, batch 1, stride 1): y = silu(a[c] x + b[c]) applied by the operand converter
-    const double2* gn_partial;   // [G][S] fp64 (sum, sumsq) partials of image 0 (sfb_groupnorm_stats_nhwc); NULL = no fusion
-    const float* gn_gamma;
-    const float* gn_beta;
-    const float* gn_film;        // (scale[Cin] | shift[Cin]) or NULL
-    int32_t gn_S, gn_G, Cin, H, W;
-    float gn_eps;
     int32_t presplit;       // tmB / tmBlo hold (hi, lo) of the weights: the converter leaves the N-side tile alone
     int32_t raw_hi;         // experiment (variant 3): feed the un-masked fp32 word as the "hi" tensor-core operand (is the hardware's tf32 read a truncation?)
 };
@@ -44,6 +37,5 @@ int conv_prof_end(cudaStream_t st);
 
 // v2: M-side operand through tensor memory, optional swap-AB (conv_tcgen05_v2.cu)
 int launch_conv_v2(const ConvGemmParams& p, int BN, bool swap, dim3 grid, cudaStream_t st);
-constexpr int kGnCoefBytes = 2048 * 8 + 256;   // (a, b) per input channel (Cin <= 2048) + (mean, rstd) of <= 32 groups
 
 }  // namespace sfb

@@ -385,41 +385,9 @@ int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int6
                                    splits, bn, stream);
 }
 
-struct GnFuse {
-    const float* partial;   // fp64 pairs, as written by sfb_groupnorm_stats_nhwc
-    int S, G;
-    float eps;
-    const float *gamma, *beta, *film;
-};
-static int conv_impl(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
-                     int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate,
-                     int splits, int bn, void* stream, const GnFuse* gn);
-
 int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
                             int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                             int accumulate, int splits, int bn, void* stream) {
-    return conv_impl(x, NB, H, W, Cin, ldx, w_packed, w_hi_lo, Cout, KH, KW, stride, pad, pad_after, bias, residual, ldr, out, ldo, accumulate, splits, bn,
-                     stream, nullptr);
-}
-
-int sfb_conv2d_gn_supported(int NB, int Cin, int G, int stride) {
-    return (precision_mode() == 1 && g_variant >= 2 && NB == 1 && stride == 1 && Cin % 32 == 0 && Cin <= 2048 && G >= 1 && G <= 32 && Cin % G == 0) ? 1 : 0;
-}
-
-int sfb_conv2d_gn_nhwc_tf32(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* gn_partial, int gn_slabs, int groups, float eps,
-                            const float* gamma, const float* beta, const float* film, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
-                            int pad, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate, int splits,
-                            void* stream) {
-    SFB_REQUIRE(gn_partial && gamma && beta, "conv2d_gn_nhwc_tf32: null pointer");
-    SFB_REQUIRE(sfb_conv2d_gn_supported(NB, Cin, groups, 1), "conv2d_gn_nhwc_tf32: needs 3xTF32 mode, batch 1, stride 1, Cin a multiple of 32 and <= 2048");
-    SFB_REQUIRE(gn_slabs >= 1 && ((uintptr_t)gn_partial & 15) == 0, "conv2d_gn_nhwc_tf32: bad statistics workspace");
-    const GnFuse gn{gn_partial, gn_slabs, groups, eps, gamma, beta, film};
-    return conv_impl(x, NB, H, W, Cin, ldx, w_packed, w_hi_lo, Cout, KH, KW, 1, pad, pad, bias, residual, ldr, out, ldo, accumulate, splits, 0, stream, &gn);
-}
-
-static int conv_impl(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
-                     int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate,
-                     int splits, int bn, void* stream, const GnFuse* gn) {
     SFB_REQUIRE(x && w_packed && out, "conv2d_nhwc_tf32: null pointer");
     SFB_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_nhwc_tf32: empty shape");
     SFB_REQUIRE(stride == 1 || stride == 2, "conv2d_nhwc_tf32: stride must be 1 or 2");
@@ -440,7 +408,6 @@ static int conv_impl(const float* x, int NB, int H, int W, int Cin, int64_t ldx,
     const int64_t P_total = (int64_t)NB * Ho * Wo;
     const bool v2 = (precision_mode() == 1 && g_variant >= 2);
     const bool swap = v2 && P_total <= 64 && bn <= 0;
-    if (gn != nullptr) SFB_REQUIRE(v2, "conv2d_gn_nhwc_tf32: the fused GroupNorm path exists in the 3xTF32 v2 kernel only");
     int tile_pix = kBM;
     if (swap) { tile_pix = 16; while (tile_pix < P_total) tile_pix *= 2; }
     p.TW = Wo >= tile_pix ? tile_pix : pow2_floor(Wo);
@@ -459,12 +426,6 @@ static int conv_impl(const float* x, int NB, int H, int W, int Cin, int64_t ldx,
     p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.out = out; p.bias = bias; p.ldo = ldo; p.accumulate = accumulate;
     p.raw_hi = (g_variant == 3) ? 1 : 0;
-    p.Cin = Cin; p.H = H; p.W = W;
-    if (gn != nullptr) {
-        p.gn_partial = reinterpret_cast<const double2*>(gn->partial);
-        p.gn_S = gn->S; p.gn_G = gn->G; p.gn_eps = gn->eps;
-        p.gn_gamma = gn->gamma; p.gn_beta = gn->beta; p.gn_film = gn->film;
-    }
     p.residual = residual; p.ldr = ldr;
     SFB_REQUIRE(residual == nullptr || (ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0), "conv2d_nhwc_tf32: residual must be 16-byte aligned");
 

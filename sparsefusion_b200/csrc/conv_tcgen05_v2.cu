@@ -68,8 +68,6 @@ __device__ __forceinline__ void phase_mark(unsigned int slot, int phase) {
     }
 }
 
-__device__ __forceinline__ float gn_silu(float x) { return x / (1.f + __expf(-x)); }   // same expression as unet_ops.cu's silu_f
-
 // SWAP == false: M-side = 128 output pixels (tmA), N-side = BN output channels (tmB).
 // SWAP == true : M-side = 128 output channels (tmB), N-side = BN output pixels (tmA, box {32, TW, TH, TN} with TW*TH*TN == BN).
 template <int BN, bool SWAP>
@@ -89,9 +87,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* bias_s = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 512);   // up to 256 floats
     int* pix_s = reinterpret_cast<int*>(smem + S * Cfg::kStageBytes + 512 + 1024);   // SWAP: linear output pixel of tile column j, or -1
-    short2* pyx_s = reinterpret_cast<short2*>(smem + S * Cfg::kStageBytes + 512 + 1024 + 256);   // SWAP + GN: (y, x) of tile column j in the output plane
-    float2* coef_s = reinterpret_cast<float2*>(smem + Cfg::kSmemBytes - 1024);   // GN fusion: (a, b) per input channel, then (mean, rstd) per group (only
-    float2* gst_s = coef_s + 2048;                                                //   allocated when p.gn_partial != nullptr: + kGnCoefBytes of dynamic smem)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
@@ -219,7 +214,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             const int tw = et % p.TW, th = (et / p.TW) % p.TH, tn = et / (p.TW * p.TH);
             const int n = n0 + tn, h = h0 + th, w = w0 + tw;
             pix_s[et] = (n < p.NB && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
-            pyx_s[et] = make_short2((short)h, (short)w);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -227,38 +221,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
         uint64_t* mside_bar = SWAP ? wfull_bar : afull_bar;   // arrival of the 128-row tile (weights in swap mode)
         uint64_t* nside_bar = SWAP ? afull_bar : wfull_bar;
         // (1) M-side row r of stage s: 8 swizzled 16-byte chunks -> hi / lo -> TMEM columns [kABase + 64 s, +32) / [+32, +64)
-        const bool gn = p.gn_partial != nullptr;
-        // GN fusion, non-swap: this thread's output pixel; the tap offset decides per k-step whether the row is image or zero padding
-        const int m_tw = r % p.TW, m_th = (r / p.TW) % p.TH, m_tn = r / (p.TW * p.TH);
-        const int m_y = h0 + m_th, m_x = w0 + m_tw;
-        const bool m_in_batch = (n0 + m_tn) < p.NB;
         auto convert_m = [&](int it) {
             const int s = it % S;
             tc::mbar_wait(&mside_bar[s], (uint32_t)(it / S) & 1u);
             const uint8_t* rowp = smem + s * Cfg::kStageBytes + r * 128;
             uint32_t hi[32], lo[32];
-            bool xform = false;
-            int cbase = 0;
-            if (!SWAP && gn) {
-                const int i = kb + it;
-                const int tap = i / p.cin_chunks;
-                cbase = (i - tap * p.cin_chunks) * kBK;
-                const int ky = tap / p.KW, kx = tap - ky * p.KW;
-                const int iy = m_y + ky - p.pad, ix = m_x + kx - p.pad;
-                xform = m_in_batch && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;   // padding rows stay exactly zero
-            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-                float f[4] = {v.x, v.y, v.z, v.w};
-                if (!SWAP && gn) {
-                    const float4 ab0 = *reinterpret_cast<const float4*>(coef_s + cbase + c * 4);       // (a, b) of channels +0, +1
-                    const float4 ab1 = *reinterpret_cast<const float4*>(coef_s + cbase + c * 4 + 2);   // +2, +3
-                    if (xform) {
-                        f[0] = gn_silu(fmaf(ab0.x, f[0], ab0.y)); f[1] = gn_silu(fmaf(ab0.z, f[1], ab0.w));
-                        f[2] = gn_silu(fmaf(ab1.x, f[2], ab1.y)); f[3] = gn_silu(fmaf(ab1.z, f[3], ab1.w));
-                    }
-                }
+                const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
@@ -280,29 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
                 float4* nraw = reinterpret_cast<float4*>(st + kABytes);
                 float4* nlo = reinterpret_cast<float4*>(st + kABytes + Cfg::kNBytes);
 #pragma unroll 2
-                int n_cbase = 0, n_oy = 0, n_ox = 0;
-                if (SWAP && gn) {
-                    const int ii = kb + it;
-                    const int tap = ii / p.cin_chunks;
-                    n_cbase = (ii - tap * p.cin_chunks) * kBK;
-                    const int ky = tap / p.KW;
-                    n_oy = ky - p.pad;
-                    n_ox = tap - ky * p.KW - p.pad;
-                }
                 for (int i = et; i < BN * 8; i += 128) {
-                    float4 v = nraw[i];
-                    if (SWAP && gn) {
-                        const int row = i >> 3;                          // tile column = output pixel
-                        const int ch = n_cbase + (((i & 7) ^ (row & 7)) << 2);   // un-swizzle: logical 16-byte chunk of this float4
-                        const short2 yx = pyx_s[row];
-                        const int iy = yx.x + n_oy, ix = yx.y + n_ox;
-                        if (pix_s[row] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                            const float4 ab0 = *reinterpret_cast<const float4*>(coef_s + ch);
-                            const float4 ab1 = *reinterpret_cast<const float4*>(coef_s + ch + 2);
-                            v.x = gn_silu(fmaf(ab0.x, v.x, ab0.y)); v.y = gn_silu(fmaf(ab0.z, v.y, ab0.w));
-                            v.z = gn_silu(fmaf(ab1.x, v.z, ab1.y)); v.w = gn_silu(fmaf(ab1.z, v.w, ab1.w));
-                        }
-                    }
+                    const float4 v = nraw[i];
                     float4 h, l;
                     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
                     h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
@@ -322,40 +272,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
         // tiles into tensor memory up front, so that once the (small) activation tiles land only their split and the MMAs remain.
         const int pre = SWAP ? (niter < S ? niter : S) : 0;
         for (int it = 0; it < pre; ++it) convert_m(it);
-        if (gn) {
-            // y = silu(a[c] x + b[c]) with a = rstd_g gamma_c (scale_c + 1), b = (beta_c - mean_g rstd_g gamma_c)(scale_c + 1) + shift_c: fold the
-            // statistics partials of the previous kernel (so: after the dependency wait), then one (a, b) per input channel
-            pdl_wait();
-            const int G = p.gn_G, Sg = p.gn_S, Cg = p.Cin / G;
-            for (int g = q; g < G; g += 4) {
-                double ts = 0.0, tss = 0.0;
-                for (int k = lane; k < Sg; k += 32) {
-                    const double2 pr = p.gn_partial[(int64_t)g * Sg + k];
-                    ts += pr.x; tss += pr.y;
-                }
-                for (int o = 16; o > 0; o >>= 1) { ts += __shfl_xor_sync(0xffffffffu, ts, o); tss += __shfl_xor_sync(0xffffffffu, tss, o); }
-                if (lane == 0) {
-                    const double cnt = (double)p.H * p.W * Cg;
-                    const double mean = ts / cnt;
-                    double var = tss / cnt - mean * mean;
-                    if (var < 0) var = 0;
-                    gst_s[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)p.gn_eps)));
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int c = et; c < p.Cin; c += 128) {
-                const float2 st = gst_s[c / Cg];
-                float a = st.y * __ldg(p.gn_gamma + c);
-                float b = __ldg(p.gn_beta + c) - st.x * a;
-                if (p.gn_film != nullptr) {
-                    const float sc = __ldg(p.gn_film + c) + 1.f;
-                    a *= sc;
-                    b = fmaf(b, sc, __ldg(p.gn_film + p.Cin + c));
-                }
-                coef_s[c] = make_float2(a, b);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
         for (int it = 0; it < pre; ++it) convert_n_and_release(it);
         for (int it = pre; it < niter; ++it) {
             convert_m(it);
@@ -455,13 +371,13 @@ template <int BN, bool SWAP>
 static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_v2_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<BN>::kSmemBytes + kGnCoefBytes));
+        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_v2_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<BN>::kSmemBytes));
         configured = true;
     }
     conv_prof_begin(st);
     trace_name(SWAP ? (BN == 16 ? "conv_v2<16,swap>" : BN == 32 ? "conv_v2<32,swap>" : "conv_v2<64,swap>")
                     : (BN == 16 ? "conv_v2<16>" : BN == 32 ? "conv_v2<32>" : BN == 64 ? "conv_v2<64>" : BN == 128 ? "conv_v2<128>" : "conv_v2<256>"));
-    launch_pdl(conv_gemm_v2_kernel<BN, SWAP>, grid, dim3(kThreads), Conv2Cfg<BN>::kSmemBytes + (p.gn_partial != nullptr ? kGnCoefBytes : 0), st, p);
+    launch_pdl(conv_gemm_v2_kernel<BN, SWAP>, grid, dim3(kThreads), Conv2Cfg<BN>::kSmemBytes, st, p);
     conv_prof_end(st);
     return check_launch("conv2d_nhwc_tf32(v2)");
 }

@@ -711,42 +711,7 @@ static inline int ew_blocks(int64_t total, int threads = 256) {
 
 using namespace sfb;
 
-// slab count of the statistics pass (a pure function of the shape: the fused conv reads the same number of partials)
-static bool gn_rows_ok(int C, int G) {
-    const int C4 = C / 4, Cg = C / G;
-    return (Cg % 4 == 0) && (C4 <= 256 ? (256 % C4 == 0) : (C4 % 256 == 0)) && (Cg / 4 <= (C4 < 256 ? C4 : 256));
-}
-static void gn_launch_stats(const float* x, int64_t ldx, int NB, int HW, int C, int G, int S, double2* partial, cudaStream_t st) {
-    if (gn_rows_ok(C, G)) SFB_LAUNCH(gn_stats_rows_kernel, dim3(S, NB), 256, 0, st, x, ldx, HW, C, G, S, partial);
-    else SFB_LAUNCH(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, S, partial);
-}
-
 extern "C" {
-
-int sfb_groupnorm_slabs(int NB, int HW, int C, int G) {
-    if (NB < 1 || HW < 1 || G < 1 || C < G) return 1;
-    int S = 1;
-    if (gn_rows_ok(C, G)) {
-        const int C4 = C / 4;
-        const int rpi = 256 / (C4 < 256 ? C4 : 256);
-        const int want = (2 * sm_count() + NB - 1) / NB;                // ~2 CTAs per SM over the batch
-        S = HW / (rpi * 2);                                             // two block iterations per slab: the pass is latency bound (measured: 8 -> 5.5 us, 2 -> 3.8 us)
-        if (S > want) S = want;
-        if (S > kGnMaxSlabs) S = kGnMaxSlabs;
-        if (S < 1) S = 1;
-    } else {
-        while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
-    }
-    return S;
-}
-
-int sfb_groupnorm_stats_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, float* partial, void* stream) {
-    SFB_REQUIRE(x && partial, "groupnorm_stats_nhwc: null pointer");
-    SFB_REQUIRE(((uintptr_t)partial & 15) == 0, "groupnorm_stats_nhwc: workspace must be 16-byte aligned");
-    SFB_REQUIRE(C % G == 0 && C % 4 == 0 && ldx % 4 == 0 && G <= kGnMaxGroups, "groupnorm_stats_nhwc: C must be a multiple of the group count (<= 32) and of 4");
-    gn_launch_stats(x, ldx, NB, HW, C, G, sfb_groupnorm_slabs(NB, HW, C, G), reinterpret_cast<double2*>(partial), as_stream(stream));
-    return check_launch("groupnorm_stats_nhwc");
-}
 
 int sfb_nchw_to_nhwc(const float* src, float* dst, int NB, int C, int H, int W, int64_t ld, int c_off, int round_tf32, void* stream) {
     SFB_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
@@ -792,8 +757,21 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     SFB_REQUIRE(G <= kGnMaxGroups, "groupnorm_nhwc: at most 32 groups");
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
     (void)counters;
-    const int S = sfb_groupnorm_slabs(NB, HW, C, G);
-    gn_launch_stats(x, ldx, NB, HW, C, G, S, partial, st);
+    const int C4 = C / 4, Cg = C / G;
+    const bool rows_ok = (Cg % 4 == 0) && (C4 <= 256 ? (256 % C4 == 0) : (C4 % 256 == 0)) && (Cg / 4 <= (C4 < 256 ? C4 : 256));
+    int S = 1;
+    if (rows_ok) {
+        const int rpi = 256 / (C4 < 256 ? C4 : 256);
+        const int want = (2 * sm_count() + NB - 1) / NB;                // ~2 CTAs per SM over the batch
+        S = HW / (rpi * 2);                                             // two block iterations per slab: the pass is latency bound (measured: 8 -> 5.5 us, 2 -> 3.8 us)
+        if (S > want) S = want;
+        if (S > kGnMaxSlabs) S = kGnMaxSlabs;
+        if (S < 1) S = 1;
+        SFB_LAUNCH(gn_stats_rows_kernel, dim3(S, NB), 256, 0, st, x, ldx, HW, C, G, S, partial);
+    } else {
+        while (S < 64 && G * NB * S * 2 <= sm_count() * 2 && HW / (S * 2) >= 8) S *= 2;
+        SFB_LAUNCH(gn_stats_kernel, dim3(G, NB, S), 256, 0, st, x, ldx, HW, C, G, S, partial);
+    }
     if (int rc = check_launch("groupnorm_nhwc(stats)")) return rc;
     const int64_t img4 = (int64_t)HW * (C / 4);
     int ab = (int)((img4 + 256 * 4 - 1) / (256 * 4));     // ~4 float4 per thread

@@ -281,7 +281,6 @@ class Unet(nn.Module):
         self.reset_parameters()
         self._plan = None  # packed weights etc., rebuilt lazily
         self.use_arena = True      # split-K conv outputs from one zero-filled buffer per evaluation (ops.ZeroArena)
-        self.fuse_groupnorm = True  # GroupNorm-apply folded into the consuming convolution where the kernel supports it (batch 1, 3xTF32)
         self._arena_floats = {}    # (nb, h, w) -> floats, measured on the first evaluation of that shape
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -385,23 +384,12 @@ class Unet(nn.Module):
             sp = pl['split'][key] = ops.split_packed_weight(pl['packed'][key])
         return sp
 
-    def _conv(self, name, x, k, stride=1, pad=0, residual=None, out=None, accumulate=False, gn=None):
+    def _conv(self, name, x, k, stride=1, pad=0, residual=None, out=None, accumulate=False):
         pl = self._plan
         w = pl['packed'][name + '.weight']
         npix = x.shape[0] * (x.shape[1] // stride) * (x.shape[2] // stride)
         return ops.conv2d_nhwc(x, w, w.shape[0], k, k, stride, pad, bias=pl['P'].get(name + '.bias'), residual=residual, out=out,
-                               accumulate=accumulate, w_split=self._split(name + '.weight', npix), gn=gn)
-
-    def _norm_conv(self, norm, conv, x, film, residual=None):
-        """Block (imagen_pytorch.py:640-656): GroupNorm -> (scale + 1, shift) -> SiLU -> 3x3 conv.  Batch-1 evaluations in 3xTF32 mode run the
-        statistics pass and ONE fused normalise+convolve launch; otherwise GroupNorm-apply is its own launch."""
-        P = self._plan['P']
-        g = self.groups
-        if self.fuse_groupnorm and ops.conv_gn_supported(x, g):
-            ws, slabs = ops.groupnorm_stats(x, g)
-            frow = None if film is None else film[0]
-            return self._conv(conv, x, 3, 1, 1, residual=residual, gn=(ws, slabs, g, 1e-5, P[norm + '.weight'], P[norm + '.bias'], frow))
-        return self._conv(conv, ops.groupnorm(x, g, P[norm + '.weight'], P[norm + '.bias'], film, True), 3, 1, 1, residual=residual)
+                               accumulate=accumulate, w_split=self._split(name + '.weight', npix))
 
     def _linear_rows(self, name, x, bias=True, round_out=False):
         """token projection [.., K] -> [.., O]: fp32 GEMV for a handful of rows, tensor cores (swap-AB tile: the rows are the N side) from 16 rows up --
@@ -420,18 +408,20 @@ class Unet(nn.Module):
         off, width = pl['film_off'][pfx]
         film = film_all[:, off:off + width]
         g = self.groups
-        h = self._norm_conv(f'{pfx}.block1.groupnorm', f'{pfx}.block1.project', x, None)
+        a1 = ops.groupnorm(x, g, P[f'{pfx}.block1.groupnorm.weight'], P[f'{pfx}.block1.groupnorm.bias'], None, True)
+        h = self._conv(f'{pfx}.block1.project', a1, 3, 1, 1)
         if f'{pfx}.cross_attn.fn.null_kv' in P:
             h = self._cross_attn(f'{pfx}.cross_attn.fn', h, c_tokens)
+        a2 = ops.groupnorm(h, g, P[f'{pfx}.block2.groupnorm.weight'], P[f'{pfx}.block2.groupnorm.bias'], film, True)
         res = self._conv(f'{pfx}.res_conv', x, 1) if f'{pfx}.res_conv.weight' in P else x
         if f'{pfx}.gca.to_k.weight' in P:
-            h2 = self._norm_conv(f'{pfx}.block2.groupnorm', f'{pfx}.block2.project', h, film)
+            h2 = self._conv(f'{pfx}.block2.project', a2, 3, 1, 1)
             pooled = ops.gca_pool(h2, P[f'{pfx}.gca.to_k.weight'], P[f'{pfx}.gca.to_k.bias'])
             w0, w2 = P[f'{pfx}.gca.net.0.weight'], P[f'{pfx}.gca.net.2.weight']
             hid = ops.linear_small(pooled, w0.reshape(w0.shape[0], -1), P[f'{pfx}.gca.net.0.bias'], post=1)
             out = ops.gate_mlp_residual(h2, hid, w2.reshape(w2.shape[0], -1), P[f'{pfx}.gca.net.2.bias'], res)   # gate GEMV + sigmoid + h*gate + res
         else:
-            out = self._norm_conv(f'{pfx}.block2.groupnorm', f'{pfx}.block2.project', h, film, residual=res)
+            out = self._conv(f'{pfx}.block2.project', a2, 3, 1, 1, residual=res)
         if taps is not None:
             taps[pfx] = out
         return out

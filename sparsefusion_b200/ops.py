@@ -154,7 +154,7 @@ def _conv_out(shape, device):
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 accumulate: bool = False, splits: int = 0, bn: int = 0, pad_after: Optional[int] = None,
-                w_split: Optional[torch.Tensor] = None, gn: Optional[tuple] = None) -> torch.Tensor:
+                w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, h, w, cin, ldx = _nhwc_meta(x)
     if pad_after is None:
         pad_after = pad
@@ -172,13 +172,6 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw:
         assert (rnb, rh, rw, rc) == (nb, ho, wo, cout)
     if w_split is not None:
         assert w_split.shape == (2,) + tuple(w_packed.shape)
-    if gn is not None:   # GroupNorm(+FiLM)+SiLU of the RAW input x folded into the operand converter: (ws, slabs, groups, eps, gamma, beta, film row or None)
-        ws, slabs, groups, eps, gamma, beta, film = gn
-        assert stride == 1 and pad_after == pad and (film is None or (film.numel() == 2 * cin and film.stride(-1) == 1))
-        lib.call('sfb_conv2d_gn_nhwc_tf32', x.data_ptr(), nb, h, w, cin, ldx, lib.fptr(ws), slabs, groups, float(eps), lib.fptr(gamma), lib.fptr(beta),
-                 None if film is None else film.data_ptr(), lib.fptr(w_packed, 'w_packed'), lib.fptr(w_split, 'w_split'), cout, kh, kw, pad,
-                 lib.fptr(bias, 'bias'), None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, lib.stream())
-        return out
     lib.call('sfb_conv2d_nhwc_tf32_ex', x.data_ptr(), nb, h, w, cin, ldx,
              lib.fptr(w_packed, 'w_packed'), lib.fptr(w_split, 'w_split'), cout, kh, kw, stride, pad, pad_after, lib.fptr(bias, 'bias'),
              None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
@@ -279,20 +272,6 @@ def _gn_counters(device, n: int) -> torch.Tensor:
         t = torch.zeros(max(n, 4096), dtype=torch.int32, device=device)
         _GN_COUNTERS[key] = t
     return t
-
-
-def groupnorm_stats(x: torch.Tensor, groups: int):
-    """statistics pass of GroupNorm alone -> (partials workspace, slab count); feed to conv2d_nhwc(gn=...)"""
-    nb, h, w, c, ldx = _nhwc_meta(x)
-    s = int(lib.load().sfb_groupnorm_slabs(nb, h * w, c, groups))
-    ws = torch.empty(4 * nb * groups * s, dtype=torch.float32, device=x.device)
-    lib.call('sfb_groupnorm_stats_nhwc', x.data_ptr(), ldx, nb, h * w, c, groups, lib.fptr(ws), lib.stream())
-    return ws, s
-
-
-def conv_gn_supported(x: torch.Tensor, groups: int, stride: int = 1) -> bool:
-    nb, _, _, c, _ = _nhwc_meta(x)
-    return bool(lib.load().sfb_conv2d_gn_supported(nb, c, groups, stride))
 
 
 def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor, film: Optional[torch.Tensor] = None,

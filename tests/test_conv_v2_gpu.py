@@ -101,34 +101,3 @@ def test_presplit_weights_match_in_kernel_split(case):
     assert torch.equal(y0, y1)
     ref = _ref(x, wt, b, stride, pad)
     assert ((y1 - ref).norm() / ref.norm()).item() < 2e-5
-
-
-@pytest.mark.parametrize('case', [(32, 32, 256, 256, 3), (16, 16, 512, 256, 3), (8, 8, 1024, 512, 3), (4, 4, 2048, 1024, 3), (4, 4, 1024, 1024, 1),
-                                  (5, 7, 64, 96, 3), (32, 32, 512, 256, 3)])
-@pytest.mark.parametrize('film', [False, True])
-def test_groupnorm_folded_into_conv(case, film):
-    """GroupNorm(8)+FiLM+SiLU applied by the conv's operand converter (one launch) vs GroupNorm kernel + conv (two launches) and vs fp64 torch:
-    covers the swap-AB (<= 64 pixels: activations on the N side) and the normal tiling, zero padding at the borders, 1x1 and 3x3 taps."""
-    from sparsefusion_b200 import ops
-    h, w, cin, cout, k = case
-    ops.set_precision('tf32x3')
-    g = torch.Generator(device='cuda').manual_seed(31 + cin + h)
-    x = torch.randn(1, h, w, cin, device='cuda', generator=g) * 2 + 0.3
-    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k) ** 0.5
-    b = torch.randn(cout, device='cuda', generator=g)
-    gamma, beta = torch.randn(cin, device='cuda', generator=g), torch.randn(cin, device='cuda', generator=g)
-    fm = torch.randn(1, 2 * cin, device='cuda', generator=g) * 0.5 if film else None
-    res = torch.randn(1, h, w, cout, device='cuda', generator=g)
-    wp = ops.pack_conv_weight(wt)
-    assert ops.conv_gn_supported(x, 8)
-    ws, slabs = ops.groupnorm_stats(x, 8)
-    fused = ops.conv2d_nhwc(x, wp, cout, k, k, 1, k // 2, bias=b, residual=res, gn=(ws, slabs, 8, 1e-5, gamma, beta, None if fm is None else fm[0]))
-    two = ops.conv2d_nhwc(ops.groupnorm(x, 8, gamma, beta, fm, True), wp, cout, k, k, 1, k // 2, bias=b, residual=res)
-    xn = F.group_norm(x.permute(0, 3, 1, 2).double(), 8, gamma.double(), beta.double(), eps=1e-5)
-    if film:
-        xn = xn * (fm.double()[:, :cin, None, None] + 1) + fm.double()[:, cin:, None, None]
-    ref = (F.conv2d(F.silu(xn), wt.double(), b.double(), padding=k // 2).permute(0, 2, 3, 1) + res.double()).float()
-    r_two = ((fused - two).norm() / two.norm()).item()
-    r_ref = ((fused - ref).norm() / ref.norm()).item()
-    print(f'{case} film={film}: fused vs two-launch {r_two:.3e}, vs fp64 {r_ref:.3e}')
-    assert r_two < 2e-5 and r_ref < 3e-5
