@@ -271,6 +271,29 @@ int sfb_ray_composite_backward(const float* z_sorted, const float* sigma, const 
 int sfb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
 
+/* ==========================================================================================
+ * section 6 -- ray generation and image-space glue of a distillation step
+ *    Replaces ~50 eager launches per sub-step of sparsefusion/distillation.py:201-241, :274-288, :307-344 (+ utils/common_utils.py:183-190,
+ *    utils/render_utils.py:40-47) and autograd's backward of them.  img [h*w, 3] pixel-major rendered colours, sil [h*w] opacity;
+ *    full-resolution tensors are planes [C][H][W] of one view.
+ * ========================================================================================== */
+/* rays of the pixel-centre NDC grid (x, y from 1 - 1/W to -1 + 1/W), un-normalised directions on the plane at depth 1 (pytorch3d ray sampler
+ * semantics): cam = centre[3] | R[9] with rows (right, up, forward); rays_o / rays_d [H*W, 3]. */
+int sfb_rays_from_camera(const float* cam, int H, int W, float focal_ndc, float* rays_o, float* rays_d, void* stream);
+/* photometric sub-step (distillation.py:210-234): value and gradient in one launch.  rgb [3][h*scale][w*scale], mask [1][h*scale][w*scale]
+ * (sampled 'nearest' at stride `scale`); sums[3] <- (sum huber colour, sum huber silhouette, sum sqrt(sil^2 + .01)) so that
+ * loss = lc * sums[0] / (3 h w) + ls * sums[1] / (h w) + lo * sums[2] / (h w); g_img [h*w,3] and g_sil [h*w] = d loss / d (img, sil). */
+int sfb_photometric_loss(const float* img, const float* sil, const float* rgb, const float* mask, int h, int w, int scale, float lambda_color,
+                         float lambda_sil, float lambda_opacity, float* sums, float* g_img, float* g_sil, void* stream);
+/* up [4][2h][2w]: bilinear x2 (align_corners = False) of the three colour planes and of the opacity (distillation.py:287-288), NCHW for the VAE */
+int sfb_upsample2x_render(const float* img, const float* sil, int h, int w, float* up, void* stream);
+/* fusion sub-step loss on the up-sampled planes and its gradient back at render resolution (through the adjoint of the bilinear x2).
+ * mode 0 (SDS, :310): weight * mean |up_rgb - target| + lo * mean sqrt(up_sil^2 + .01); mode 1 (EFT bootstrap, :316-329): lc * mean huber(up_rgb,
+ * target) + ls * mean huber(up_sil, mean_c target > .1) + the same opacity term.  sums[3] as above (colour, silhouette, opacity sums over H*W
+ * resp. 3*H*W elements); g_up [4][H][W] scratch; g_img [h*w,3], g_sil [h*w] outputs. */
+int sfb_fusion_loss(const float* up, const float* target, int H, int W, int mode, float weight, float lambda_color, float lambda_sil,
+                    float lambda_opacity, float* sums, float* g_up, int h, int w, float* g_img, float* g_sil, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,8 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as lib
-from .plms import PLMSSampler
+from . import image_glue as glue
+from .plms import PLMSSampler, _log_snr as plms_log_snr, _sigmoid as plms_sigmoid
 
 
 def normalize(x):  # utils/common_utils.py:9-13
@@ -123,12 +124,13 @@ class FlatAdam:
 class Distiller:
     def __init__(self, ngp, vae, vldm, opt, cache: SceneCache, *, z_scale_factor=0.18215, plms_steps=50, start_fusion_step=1000,
                  lambda_color=1.0, lambda_sil=1.0, lambda_opacity=1e-3, seed=0, rank=0, world_size=1, process_group=None,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, fused_glue=True):
         self.ngp, self.vae, self.vldm, self.opt, self.cache = ngp, vae, vldm, opt, cache
         self.z_scale_factor = z_scale_factor
         self.start_fusion_step = start_fusion_step
         self.lambda_color, self.lambda_sil, self.lambda_opacity = lambda_color, lambda_sil, lambda_opacity
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.fused_glue = fused_glue   # image-space losses + their gradients as fused kernels (image_glue.py) instead of ~50 eager launches + autograd
         self.sampler = PLMSSampler(vldm, plms_steps, use_cuda_graph=use_cuda_graph)          # distillation.py:160
         self.optimizer = FlatAdam(ngp, lr=5e-4)                                              # :165-166
         # the reference draws from torch's global CPU generator (:185,:263,:303); a private generator with the same draw
@@ -139,6 +141,16 @@ class Distiller:
         self.last = {}
 
     # ------------------------------------------------------------------------------------------------
+    def _render_raw(self, rays_o, rays_d, which='A'):
+        """(image [N,3], weights_sum [N], hw) with the autograd graph of the render attached"""
+        kw = self.render_kw
+        if self.render_noise is not None:
+            pn, un = self.render_noise(which)
+            kw = dict(kw, perturb_noise=pn, pdf_noise=un)
+        out = self.ngp.render(rays_o[None], rays_d[None], **kw)
+        n = rays_o.shape[0]
+        return out['image'].reshape(n, 3), out['weights_sum'].reshape(n), int(round(n ** 0.5))
+
     def _render(self, rays_o, rays_d, which='A'):
         kw = self.render_kw
         if self.render_noise is not None:
@@ -158,6 +170,16 @@ class Distiller:
         self.ngp.train()
         if self.opt.cuda_ray and itr % 16 == 0:                                               # :181-182
             self.ngp.update_extra_state()
+        if self.fused_glue:
+            img, ws, hw = self._render_raw(c.input_rays_o[idx], c.input_rays_d[idx], 'A')
+            loss, g_img, g_ws = glue.photometric_loss(img.detach(), ws.detach(), c.input_rgb[idx], c.input_mask[idx], hw, hw, int(self.opt.hw_scale),
+                                                      self.lambda_color, self.lambda_sil, self.lambda_opacity)        # :216-234 value + gradient
+            self.optimizer.zero_grad()                                                        # :244
+            torch.autograd.backward((img, ws), (g_img, g_ws))
+            self.optimizer.step(grad_scale=self.optimizer.sync_grads(self.world_size, self.pg))
+            self.optimizer.scheduler_step()                                                   # :247
+            self.last['photo_loss'] = loss
+            return loss
         image, sil = self._render(c.input_rays_o[idx], c.input_rays_d[idx], 'A')
         scale = 1.0 / self.opt.hw_scale
         batch_rgb = F.interpolate(c.input_rgb[idx:idx + 1], scale_factor=scale)               # :216 (nearest)
@@ -184,6 +206,8 @@ class Distiller:
         vi = shard_target_view(perm, self.rank)                                               # :264
         u = torch.rand(1, generator=self.gen)                                                 # :303 (drawn every step to keep the stream aligned)
         feats = c.target_features[vi:vi + 1]
+        if self.fused_glue and int(self.opt.hw_scale) == 2:
+            return self._fusion_substep_fused(itr, max_thres, vi, u, feats)
         image, sil = self._render(c.target_rays_o[vi], c.target_rays_d[vi], 'B')
         image = F.interpolate(image, scale_factor=self.opt.hw_scale, mode='bilinear')         # :287
         sil = F.interpolate(sil, scale_factor=self.opt.hw_scale, mode='bilinear')             # :288
@@ -208,6 +232,29 @@ class Distiller:
         self.optimizer.step(grad_scale=self.optimizer.sync_grads(self.world_size, self.pg))   # :352
         self.last['fusion_loss'] = loss.detach()
         return loss.detach()
+
+    def _fusion_substep_fused(self, itr, max_thres, vi, u, feats):
+        """the same sub-step with the image-space work in three kernels: bilinear x2 to NCHW (for the VAE), loss value + gradient at full
+        resolution, adjoint of the bilinear back to the render's [N,3] / [N] outputs"""
+        c = self.cache
+        img, ws, hw = self._render_raw(c.target_rays_o[vi], c.target_rays_d[vi], 'B')
+        up = glue.upsample2x_render(img.detach(), ws.detach(), hw, hw)                         # :287-288, planes (r, g, b, opacity)
+        if itr > self.start_fusion_step:                                                      # :294
+            with torch.no_grad():
+                latents = self.vae.encode(normalize(up[None, :3])).mode() * self.z_scale_factor          # :299
+                if max_thres is None:
+                    max_thres = u.clamp(min=0.0, max=0.99).item()                             # :303
+                pred_x0, _, _, _ = self.sampler.sample(latents, cond_images=feats, use_tqdm=False, return_noise=True, max_thres=max_thres)   # :304
+                pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
+            weight = 1.0 - plms_sigmoid(plms_log_snr(float(max_thres)))                      # 1 - alpha_cumprod of the run's first noise level (:307)
+            loss, g_img, g_ws = glue.fusion_loss(up, pred_img[0], hw, hw, 'sds', weight, self.lambda_color, self.lambda_sil, self.lambda_opacity)
+            self.last['unet_calls'] = self.sampler.last_unet_calls
+        else:                                                                                 # EFT bootstrap :316-329
+            loss, g_img, g_ws = glue.fusion_loss(up, c.target_eft_image[vi], hw, hw, 'eft', 1.0, self.lambda_color, self.lambda_sil, self.lambda_opacity)
+        torch.autograd.backward((img, ws), (g_img, g_ws))                                     # :345
+        self.optimizer.step(grad_scale=self.optimizer.sync_grads(self.world_size, self.pg))   # :352
+        self.last['fusion_loss'] = loss
+        return loss
 
     def step(self, itr: int, max_thres: Optional[float] = None):
         """one iteration of the reference's main loop (distillation.py:174-352); returns the two losses as device scalars"""

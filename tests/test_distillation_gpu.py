@@ -14,8 +14,9 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
+@pytest.mark.parametrize('fused_glue', [True, False], ids=['glue-kernels', 'glue-torch'])   # image-space losses: fused kernels / eager torch + autograd
 @pytest.mark.parametrize('itr', [5, 1500])   # EFT bootstrap phase / SDS phase (start_fusion_step = 1000)
-def test_step_matches_restatement(itr):
+def test_step_matches_restatement(itr, fused_glue):
     from _helpers import device_level_scales
     from oracle import distill_oracle as do, ngp_oracle as no, unet_oracle as uo
     from sparsefusion_b200.distillation import Distiller, SceneCache
@@ -55,7 +56,7 @@ def test_step_matches_restatement(itr):
                 dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11)
+    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11, fused_glue=fused_glue)
     src = uo.NoiseSource(seed=5)
     dist.sampler.noise_fn = lambda t: src(t.cpu()).to(t.device)
     dist.render_noise = lambda k: tuple(t.cuda() for t in noises[k])
