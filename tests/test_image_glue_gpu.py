@@ -43,8 +43,8 @@ def test_photometric_loss_and_gradients(hw):
     b = sil.double().requires_grad_(True)
     image = a.reshape(1, hw, hw, 3).permute(0, 3, 1, 2)
     s = b.reshape(1, 1, hw, hw)
-    ref = lc * _huber(image, F.interpolate(rgb[None].double(), scale_factor=0.5)).abs().mean() \\
-        + ls * _huber(s, F.interpolate(mask[None].double(), scale_factor=0.5)).abs().mean() + lo * torch.sqrt(s ** 2 + .01).mean()
+    ref = (lc * _huber(image, F.interpolate(rgb[None].double(), scale_factor=0.5)).abs().mean()
+           + ls * _huber(s, F.interpolate(mask[None].double(), scale_factor=0.5)).abs().mean() + lo * torch.sqrt(s ** 2 + .01).mean())
     ref.backward()
     assert abs(loss.item() - ref.item()) < 2e-6 * abs(ref.item())
     assert _rel(g_img, a.grad) < 2e-6 and _rel(g_sil, b.grad) < 2e-6
