@@ -282,6 +282,8 @@ class Unet(nn.Module):
         self._plan = None  # packed weights etc., rebuilt lazily
         self.use_arena = True      # split-K conv outputs from one zero-filled buffer per evaluation (ops.ZeroArena)
         self._arena_floats = {}    # (nb, h, w) -> floats, measured on the first evaluation of that shape
+        self.parallel_res_conv = True   # res_conv on a side stream = a parallel branch of the captured graph (see _resnet)
+        self._side = {}
 
     # ------------------------------------------------------------------------------------------ parameters
     @torch.no_grad()
@@ -402,25 +404,50 @@ class Unet(nn.Module):
             return ops.linear_small(x, w.reshape(w.shape[0], -1), b, round_to_tf32=round_out)
         return ops.linear_tc(x, pl['packed'][name + '.weight'], w.shape[0], bias=b, w_split=self._split(name + '.weight', rows))
 
+    def _side_stream(self, device):
+        key = torch.device(device).index
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
+
     def _resnet(self, pfx, x, film_all, c_tokens, taps=None):
         pl = self._plan
         P = pl['P']
         off, width = pl['film_off'][pfx]
         film = film_all[:, off:off + width]
         g = self.groups
+        # res_conv(x) only depends on the block input and is consumed at the very end of the block: issue it on a side stream, so that in the
+        # captured graph it is a parallel branch running in the shadow of the GroupNorm launches instead of one more link of the dependent chain
+        join = None
+        if f'{pfx}.res_conv.weight' in P:
+            if self.parallel_res_conv:
+                main = torch.cuda.current_stream()
+                side = self._side_stream(x.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    res = self._conv(f'{pfx}.res_conv', x, 1)
+                res.record_stream(main)
+                join = side
+            else:
+                res = self._conv(f'{pfx}.res_conv', x, 1)
+        else:
+            res = x
         a1 = ops.groupnorm(x, g, P[f'{pfx}.block1.groupnorm.weight'], P[f'{pfx}.block1.groupnorm.bias'], None, True)
         h = self._conv(f'{pfx}.block1.project', a1, 3, 1, 1)
         if f'{pfx}.cross_attn.fn.null_kv' in P:
             h = self._cross_attn(f'{pfx}.cross_attn.fn', h, c_tokens)
         a2 = ops.groupnorm(h, g, P[f'{pfx}.block2.groupnorm.weight'], P[f'{pfx}.block2.groupnorm.bias'], film, True)
-        res = self._conv(f'{pfx}.res_conv', x, 1) if f'{pfx}.res_conv.weight' in P else x
         if f'{pfx}.gca.to_k.weight' in P:
             h2 = self._conv(f'{pfx}.block2.project', a2, 3, 1, 1)
             pooled = ops.gca_pool(h2, P[f'{pfx}.gca.to_k.weight'], P[f'{pfx}.gca.to_k.bias'])
             w0, w2 = P[f'{pfx}.gca.net.0.weight'], P[f'{pfx}.gca.net.2.weight']
             hid = ops.linear_small(pooled, w0.reshape(w0.shape[0], -1), P[f'{pfx}.gca.net.0.bias'], post=1)
+            if join is not None:
+                torch.cuda.current_stream().wait_stream(join)
             out = ops.gate_mlp_residual(h2, hid, w2.reshape(w2.shape[0], -1), P[f'{pfx}.gca.net.2.bias'], res)   # gate GEMV + sigmoid + h*gate + res
         else:
+            if join is not None:
+                torch.cuda.current_stream().wait_stream(join)
             out = self._conv(f'{pfx}.block2.project', a2, 3, 1, 1, residual=res)
         if taps is not None:
             taps[pfx] = out
