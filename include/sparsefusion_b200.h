@@ -58,7 +58,8 @@ int sfb_trace_names(char* out, int capacity);
  * 6 epilogue done) of launch i < capacity.  NULL unbinds. */
 int sfb_conv_phase_trace(unsigned long long* device_buf, unsigned int capacity);
 /* optional code paths (default all on): bit 0 = the NGP MLP weight gradients run as 3xTF32 tcgen05 GEMMs over the feature-major tapes
- * (cleared: the fp32 SIMT outer-product kernel).  Both agree to fp32 rounding; the switch exists for A/B measurement and tests. */
+ * (cleared: the fp32 SIMT outer-product kernel); bit 1 = batch-1 GroupNorm as ONE launch with a software grid barrier between the statistics
+ * and the normalisation (cleared: statistics kernel + apply kernel).  Variants agree to fp32 rounding; the switch exists for A/B measurement and tests. */
 int sfb_set_fusion(int mask);
 /* number of kernels this library has launched so far in this process (bench.py's "gpu_launches") */
 uint64_t sfb_launch_count(void);

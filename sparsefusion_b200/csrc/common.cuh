@@ -43,6 +43,7 @@ void phase_bind_conv_v2(unsigned long long* buf, unsigned int cap);
 // optional paths (sfb_set_fusion): bit 0 = NGP MLP weight gradients as tcgen05 GEMMs (off: the SIMT outer-product kernel)
 int fusion_mask();
 static inline bool wgrad_tc_enabled() { return (fusion_mask() & 1) != 0; }
+static inline bool gn_grid_enabled() { return (fusion_mask() & 2) != 0; }   // single-launch GroupNorm with a software grid barrier (batch 1)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

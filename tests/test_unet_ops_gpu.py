@@ -37,15 +37,27 @@ def test_pixel_shuffle_silu():
 
 
 @pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
-                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32)])
+                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32), (1, 16, 16, 512, 8), (1, 8, 8, 1024, 8), (1, 8, 8, 2048, 8), (1, 4, 4, 1024, 8),
+                                   (1, 16, 16, 768, 8), (1, 3, 5, 256, 8), (1, 32, 32, 128, 32)])
+@pytest.fixture(params=[0x7fffffff, 0x7fffffff & ~2], ids=['gn-grid-barrier', 'gn-two-launch'])
+def gn_path(request):
+    """batch-1 GroupNorm: single launch with a software grid barrier / statistics kernel + apply kernel (sfb_set_fusion bit 1)"""
+    from sparsefusion_b200 import _lib as lib
+    lib.call('sfb_set_fusion', request.param)
+    yield request.param
+    lib.call('sfb_set_fusion', 0x7fffffff)
+
+
 @pytest.mark.parametrize('film', [False, True])
-def test_groupnorm_film_silu(shape, film):
+def test_groupnorm_film_silu(shape, film, gn_path):
     from sparsefusion_b200 import ops
     nb, h, w, c, g = shape
     x = torch.randn(nb, h, w, c, device='cuda') * 3 + 0.7
     gamma, beta = torch.randn(c, device='cuda'), torch.randn(c, device='cuda')
     fm = torch.randn(nb, 2 * c, device='cuda') if film else None
     y = ops.groupnorm(x, g, gamma, beta, fm, silu=True)
+    y_again = ops.groupnorm(x, g, gamma, beta, fm, silu=True)          # the barrier words must be reusable launch after launch
+    assert torch.equal(y, y_again)
     ref = F.group_norm(x.permute(0, 3, 1, 2).double(), g, gamma.double(), beta.double(), eps=1e-5)
     if film:
         sc, sh = fm.double()[:, :c, None, None], fm.double()[:, c:, None, None]
