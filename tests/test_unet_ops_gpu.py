@@ -36,9 +36,6 @@ def test_pixel_shuffle_silu():
     _close(ops.pixel_shuffle_silu(y), ref, 1e-5)
 
 
-@pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
-                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32), (1, 16, 16, 512, 8), (1, 8, 8, 1024, 8), (1, 8, 8, 2048, 8), (1, 4, 4, 1024, 8),
-                                   (1, 16, 16, 768, 8), (1, 3, 5, 256, 8), (1, 32, 32, 128, 32)])
 @pytest.fixture(params=[0x7fffffff, 0x7fffffff & ~2], ids=['gn-grid-barrier', 'gn-two-launch'])
 def gn_path(request):
     """batch-1 GroupNorm: single launch with a software grid barrier / statistics kernel + apply kernel (sfb_set_fusion bit 1)"""
@@ -48,6 +45,9 @@ def gn_path(request):
     lib.call('sfb_set_fusion', 0x7fffffff)
 
 
+@pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
+                                   (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32), (1, 16, 16, 512, 8), (1, 8, 8, 1024, 8), (1, 8, 8, 2048, 8), (1, 4, 4, 1024, 8),
+                                   (1, 16, 16, 768, 8), (1, 3, 5, 256, 8), (1, 32, 32, 128, 32)])
 @pytest.mark.parametrize('film', [False, True])
 def test_groupnorm_film_silu(shape, film, gn_path):
     from sparsefusion_b200 import ops
