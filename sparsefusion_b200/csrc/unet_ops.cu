@@ -266,23 +266,6 @@ __global__ void __launch_bounds__(256) gn_grid_kernel(const float* __restrict__ 
         }
         __syncthreads();
     }
-    // the affine / FiLM coefficients of this thread's column(s) do not depend on the statistics: fetch them before waiting at the barrier
-    float4 ga[2], be[2], sc[2], sh[2];
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        ga[pass] = be[pass] = sh[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sc[pass] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (pass < passes) {
-            const int c = (pass * 256 + tc) * 4;
-            ga[pass] = __ldg(reinterpret_cast<const float4*>(gamma + c));
-            be[pass] = __ldg(reinterpret_cast<const float4*>(beta + c));
-            if (film) {
-                const float4 f0 = __ldg(reinterpret_cast<const float4*>(film + c));
-                sh[pass] = __ldg(reinterpret_cast<const float4*>(film + C + c));
-                sc[pass] = make_float4(f0.x + 1.f, f0.y + 1.f, f0.z + 1.f, f0.w + 1.f);
-            }
-        }
-    }
     // ---- grid barrier
     if (threadIdx.x == 0) {
         const unsigned int gen = sh_gen;
@@ -323,13 +306,15 @@ __global__ void __launch_bounds__(256) gn_grid_kernel(const float* __restrict__ 
         if (pass < passes && p < p1) {
             const int c = (pass * 256 + tc) * 4;
             const float2 st = st_sh[c / Cg];
-            const int ps = pass < 2 ? pass : 1;
-            const float4 g4 = ga[ps], b4 = be[ps], s4 = sc[ps], h4 = sh[ps];
-            float o[4] = {(v[k].x - st.x) * st.y * g4.x + b4.x, (v[k].y - st.x) * st.y * g4.y + b4.y, (v[k].z - st.x) * st.y * g4.z + b4.z,
-                          (v[k].w - st.x) * st.y * g4.w + b4.w};
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float o[4] = {(v[k].x - st.x) * st.y * ga.x + be.x, (v[k].y - st.x) * st.y * ga.y + be.y, (v[k].z - st.x) * st.y * ga.z + be.z,
+                          (v[k].w - st.x) * st.y * ga.w + be.w};
             if (film) {
-                o[0] = o[0] * s4.x + h4.x; o[1] = o[1] * s4.y + h4.y;
-                o[2] = o[2] * s4.z + h4.z; o[3] = o[3] * s4.w + h4.w;
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + c));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + C + c));
+                o[0] = o[0] * (sc.x + 1.f) + sh.x; o[1] = o[1] * (sc.y + 1.f) + sh.y;
+                o[2] = o[2] * (sc.z + 1.f) + sh.z; o[3] = o[3] * (sc.w + 1.f) + sh.w;
             }
             if (act) {
 #pragma unroll
@@ -906,7 +891,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
         const int cols = C4 < 256 ? C4 : 256, passes = C4 < 256 ? 1 : C4 / 256, rpi = 256 / cols;
         const int max_rows = (kGnGridItems / passes) * rpi;                     // pixel rows one CTA can hold
         int S = max_rows > 0 ? (HW + max_rows - 1) / max_rows : 1 << 30;
-        if (passes <= 2 && S <= kGnGridMaxCtas && S <= sm_count()) {
+        if (passes <= kGnGridItems && S <= kGnGridMaxCtas && S <= sm_count()) {
             // spread over more CTAs when there is room (shorter per-CTA chains), keeping every slab non-empty
             while (S * 2 <= kGnGridMaxCtas && S * 2 <= sm_count() && HW / (S * 2) >= rpi) S *= 2;
             if (S > HW) S = HW;
