@@ -259,6 +259,13 @@ int sfb_ray_coarse_z(const float* rays_o, const float* rays_d, const float* aabb
 /* :381-395 (+ sample_pdf :15-49) + :404-405: coarse weights -> inverse-CDF samples -> merged, sorted depths z_sorted [N,128] */
 int sfb_ray_resample(const float* z_coarse, const float* sigma_coarse, const float* nears, const float* fars, const float* u, int det,
                      uint32_t N, uint32_t num_steps, uint32_t upsample_steps, float* z_sorted, void* stream);
+/* same, also returning the 64 importance depths in draw order (z_new [N,64]) and, per sorted slot, where it came from (src_of [N,128] uint8:
+ * t < 64 = coarse sample t, 64 + t = importance sample t).  With sfb_ray_gather_sorted the renderer evaluates the field once per sample:
+ * coarse pass (sigma, rgb at the 64 stratified depths), importance pass (the 64 new depths), then this gather into sorted order. */
+int sfb_ray_resample_ex(const float* z_coarse, const float* sigma_coarse, const float* nears, const float* fars, const float* u, int det, uint32_t N,
+                        uint32_t num_steps, uint32_t upsample_steps, float* z_sorted, float* z_new, uint8_t* src_of, void* stream);
+int sfb_ray_gather_sorted(const uint8_t* src_of, const float* sigma_coarse, const float* rgb_coarse, const float* sigma_new, const float* rgb_new,
+                          uint32_t N, uint32_t T, float* sigma, float* rgb, void* stream);
 /* :414-456: weights = alpha * cumprod(1 - alpha + 1e-15); image [N,3] (+ (1-ws)*bg_color), depth [N], weights_sum [N] */
 int sfb_ray_composite_forward(const float* z_sorted, const float* sigma, const float* rgb, const float* nears, const float* fars,
                               float bg_color, uint32_t N, uint32_t T, float* image, float* depth, float* weights_sum, void* stream);

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) ray_coarse_z_kernel(const float* __restri
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_resample_kernel(const float* __restrict__ z_coarse, const float* __restrict__ sigma_c,
                                                                           const float* __restrict__ nears, const float* __restrict__ fars,
                                                                           const float* __restrict__ u_in, int det, uint32_t N,
-                                                                          float* __restrict__ z_sorted) {
+                                                                          float* __restrict__ z_sorted, float* __restrict__ z_new,
+                                                                          uint8_t* __restrict__ src_of) {
     __shared__ float s_zc[kWarpsPerBlock][kTc];
     __shared__ float s_mid[kWarpsPerBlock][kTc];
     __shared__ float s_cdf[kWarpsPerBlock][kTc];
@@ -148,7 +149,32 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_resample_kernel(const
         }
         out[pc] = c;
         out[pf] = f;
+        if (src_of != nullptr) {   // where each sorted slot came from: coarse sample t (< 64) or importance sample t (64 + t)
+            src_of[(size_t)n * kT + pc] = (uint8_t)t;
+            src_of[(size_t)n * kT + pf] = (uint8_t)(kTc + t);
+        }
+        if (z_new != nullptr) z_new[(size_t)n * kTf + t] = f;
     }
+}
+
+// sigma / rgb of the 128 sorted samples assembled from the coarse pass (64) and the importance pass (64) through src_of: the field is a pure
+// function of the sample position, so the values of the coarse samples need not be evaluated a second time (the reference gathers its coarse
+// sigmas the same way, renderer_df.py:405-416).  One thread per sorted sample.
+__global__ void ray_gather_sorted_kernel(const uint8_t* __restrict__ src_of, const float* __restrict__ sig_c, const float* __restrict__ rgb_c,
+                                         const float* __restrict__ sig_n, const float* __restrict__ rgb_n, uint32_t N, float* __restrict__ sigma,
+                                         float* __restrict__ rgb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * kT) return;
+    const size_t n = i / kT;
+    const int s = src_of[i];
+    const bool coarse = s < kTc;
+    const size_t j = n * (size_t)kTc + (coarse ? s : s - kTc);
+    const float* sp = coarse ? sig_c : sig_n;
+    const float* cp = coarse ? rgb_c : rgb_n;
+    sigma[i] = sp[j];
+    rgb[i * 3 + 0] = cp[j * 3 + 0];
+    rgb[i * 3 + 1] = cp[j * 3 + 1];
+    rgb[i * 3 + 2] = cp[j * 3 + 2];
 }
 
 // ------------------------------------------------------------------------------------------------ compositing
@@ -290,8 +316,29 @@ int sfb_ray_resample(const float* z_coarse, const float* sigma_coarse, const flo
     SFB_REQUIRE(z_coarse && sigma_coarse && nears && fars && z_sorted && (det || u), "ray_resample: null pointer");
     SFB_REQUIRE(num_steps == (uint32_t)kTc && upsample_steps == (uint32_t)kTf, "ray_resample: built for 64 + 64 samples per ray");
     ray_resample_kernel<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_coarse, sigma_coarse, nears, fars, u, det,
-                                                                                                          N, z_sorted);
+                                                                                                          N, z_sorted, nullptr, nullptr);
     return check_launch("ray_resample");
+}
+
+int sfb_ray_resample_ex(const float* z_coarse, const float* sigma_coarse, const float* nears, const float* fars, const float* u, int det, uint32_t N,
+                        uint32_t num_steps, uint32_t upsample_steps, float* z_sorted, float* z_new, uint8_t* src_of, void* stream) {
+    if (N == 0) return SFB_OK;
+    SFB_REQUIRE(z_coarse && sigma_coarse && nears && fars && z_sorted && z_new && src_of && (det || u), "ray_resample_ex: null pointer");
+    SFB_REQUIRE(num_steps == (uint32_t)kTc && upsample_steps == (uint32_t)kTf, "ray_resample_ex: built for 64 + 64 samples per ray");
+    ray_resample_kernel<<<ceil_div(N, (uint32_t)kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(z_coarse, sigma_coarse, nears, fars, u, det,
+                                                                                                          N, z_sorted, z_new, src_of);
+    return check_launch("ray_resample_ex");
+}
+
+int sfb_ray_gather_sorted(const uint8_t* src_of, const float* sigma_coarse, const float* rgb_coarse, const float* sigma_new, const float* rgb_new,
+                          uint32_t N, uint32_t T, float* sigma, float* rgb, void* stream) {
+    if (N == 0) return SFB_OK;
+    SFB_REQUIRE(src_of && sigma_coarse && rgb_coarse && sigma_new && rgb_new && sigma && rgb, "ray_gather_sorted: null pointer");
+    SFB_REQUIRE(T == (uint32_t)kT, "ray_gather_sorted: built for 128 samples per ray");
+    const size_t total = (size_t)N * kT;
+    ray_gather_sorted_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src_of, sigma_coarse, rgb_coarse, sigma_new, rgb_new, N, sigma,
+                                                                                            rgb);
+    return check_launch("ray_gather_sorted");
 }
 
 int sfb_ray_composite_forward(const float* z_sorted, const float* sigma, const float* rgb, const float* nears, const float* fars, float bg_color,

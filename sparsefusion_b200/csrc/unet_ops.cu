@@ -893,6 +893,7 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
         int S = max_rows > 0 ? (HW + max_rows - 1) / max_rows : 1 << 30;
         if (passes <= kGnGridItems && S <= kGnGridMaxCtas && S <= sm_count()) {
             // spread over more CTAs when there is room (shorter per-CTA chains), keeping every slab non-empty
+            // (measured per launch in the replayed graph: 11.6 us with the minimum CTA count, 9.8 at <= 32, 8.9 at <= 128)
             while (S * 2 <= kGnGridMaxCtas && S * 2 <= sm_count() && HW / (S * 2) >= rpi) S *= 2;
             if (S > HW) S = HW;
             SFB_LAUNCH(gn_grid_kernel, dim3(S), 256, 0, st, x, ldx, HW, C, G, eps, gamma, beta, film, partial, counters, y, ldy, act_silu,

@@ -39,13 +39,18 @@ class _RunRender(torch.autograd.Function):
         zc = torch.empty(N, 64, device=dev)
         lin = torch.linspace(0.0, 1.0, 64, device=dev)
         lib.call('sfb_ray_coarse_z', f(rays_o), f(rays_d), f(aabb), float(min_near), f(lin), f(perturb_noise), N, 64, f(nears), f(fars), f(zc), st)
-        sig_c = torch.empty(N, 64, device=dev)
+        # the field is evaluated ONCE per sample: coarse pass (sigma + rgb at the 64 stratified depths), importance pass (the 64 new depths),
+        # then a gather into sorted order -- the values of the coarse samples are the same numbers a second evaluation would produce
+        sig_c, rgb_c = torch.empty(N, 64, device=dev), torch.empty(N, 64, 3, device=dev)
         args = (f(emb), lib.iptr(enc.offsets), S, H, bound, f(w0), f(b0), f(w1), f(b1), f(w2), f(b2))
-        lib.call('sfb_ngp_field_forward', None, f(rays_o), f(rays_d), f(zc), 64, N * 64, *args, f(sig_c), None, st)
-        zs = torch.empty(N, 128, device=dev)
-        lib.call('sfb_ray_resample', f(zc), f(sig_c), f(nears), f(fars), f(pdf_u), 0, N, 64, 64, f(zs), st)
+        lib.call('sfb_ngp_field_forward', None, f(rays_o), f(rays_d), f(zc), 64, N * 64, *args, f(sig_c), f(rgb_c), st)
+        zs, zn = torch.empty(N, 128, device=dev), torch.empty(N, 64, device=dev)
+        src_of = torch.empty(N, 128, dtype=torch.uint8, device=dev)
+        lib.call('sfb_ray_resample_ex', f(zc), f(sig_c), f(nears), f(fars), f(pdf_u), 0, N, 64, 64, f(zs), f(zn), src_of.data_ptr(), st)
+        sig_n, rgb_n = torch.empty(N, 64, device=dev), torch.empty(N, 64, 3, device=dev)
+        lib.call('sfb_ngp_field_forward', None, f(rays_o), f(rays_d), f(zn), 64, N * 64, *args, f(sig_n), f(rgb_n), st)
         sigma, rgb = torch.empty(N, 128, device=dev), torch.empty(N, 128, 3, device=dev)
-        lib.call('sfb_ngp_field_forward', None, f(rays_o), f(rays_d), f(zs), 128, N * 128, *args, f(sigma), f(rgb), st)
+        lib.call('sfb_ray_gather_sorted', src_of.data_ptr(), f(sig_c), f(rgb_c), f(sig_n), f(rgb_n), N, 128, f(sigma), f(rgb), st)
         image, depth, ws = torch.empty(N, 3, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
         lib.call('sfb_ray_composite_forward', f(zs), f(sigma), f(rgb), f(nears), f(fars), float(bg_color), N, 128, f(image), f(depth), f(ws), st)
         ctx.save_for_backward(rays_o, rays_d, zs, sigma, rgb, nears, fars, emb, w0, b0, w1, b1, w2, b2)
