@@ -87,6 +87,7 @@ def unet_trace(out):
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
     torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)
     ops.set_precision('tf32x3')
+    unet.parallel_res_conv = 'parallel' in sys.argv      # per-kernel attribution needs a single dependency chain
     unet.prepare()
     x, cond, t = torch.randn(1, 4, 32, 32, device='cuda'), torch.randn(1, 256, 32, 32, device='cuda'), torch.full((1,), 0.3, device='cuda')
     runner = UnetGraph(unet)
