@@ -124,7 +124,9 @@ def build_gpu(rank, world, device):
     ngp = ngp.to(device).train()
     scene = SceneCache(**synthetic_scene(seed=0))
     pg = torch.distributed.group.WORLD if world > 1 else None
-    return Distiller, dict(ngp=ngp, vae=vae, vldm=ddpm, opt=opt), scene, dict(seed=0, rank=rank, world_size=world, process_group=pg)
+    from sparsefusion_b200.lpips_vgg import PerceptualLoss
+    percep = PerceptualLoss('vgg', device=device, seed=0)                       # distillation.py:161 (random weights: see config.lpips)
+    return Distiller, dict(ngp=ngp, vae=vae, vldm=ddpm, opt=opt), scene, dict(seed=0, rank=rank, world_size=world, process_group=pg, percep=percep)
 
 
 def run_gpu(args):
@@ -329,7 +331,7 @@ def run_gpu(args):
                'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, 7.46 MB NGP-gradient all-reduce per sub-step',
                           'unet_evals_per_step_mean': round(float(np.mean(n_calls)), 2) if n_calls else None,
                           'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
-                          'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'lpips': 'excluded in every arm (un-vendored dependency)',
+                          'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored',
                           'precision_mode': ops.get_precision()},
                'clocks': clk, 'gpu_launches': int(launches),
                'e2e': None if e2e_val is None else {'value': round(e2e_val, 4), 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
@@ -383,6 +385,8 @@ class CpuPort:
         self.threads = self._pick_threads()
         self.vae = AutoencoderKL().eval()
         self.img = torch.rand(1, 3, 256, 256)
+        from oracle import lpips_oracle as lo
+        self.lo, self.lp = lo, lo.make_params(0)
         self.p = {k: v.clone().requires_grad_(True) for k, v in no.make_field_params(seed=0).items()}
         ro, rd = no.camera_rays(no.circle_cameras(64)[3], 128, 128)
         sel = np.random.default_rng(0).choice(ro.shape[0], ray_sample, replace=False)
@@ -413,9 +417,13 @@ class CpuPort:
         with torch.no_grad():
             t0 = time.perf_counter(); self.uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c); t_unet = time.perf_counter() - t0
         t_vae = None
-        if with_vae:
+        if with_vae:   # VAE encode + decode and the perceptual term (forward of both images, backward to the rendered one): input independent costs
             with torch.no_grad():
                 t0 = time.perf_counter(); z = self.vae.encode(self.img * 2 - 1).mode(); self.vae.decode(z); t_vae = time.perf_counter() - t0
+            a = self.img.clone().requires_grad_(True)
+            t0 = time.perf_counter()
+            self.lo.lpips(self.lp, 2 * a - 1, 2 * self.img.flip(-1) - 1).sum().backward()
+            t_vae += time.perf_counter() - t0
         for v in self.p.values():
             v.grad = None
         n = self.ray_sample
@@ -460,10 +468,10 @@ def run_reference(args):
            'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': K, 'warmup': W, 'ms_per_step': round(step_s * 1e3, 1), 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': WORKLOAD, 'parallelism': f'host CPU, {port.threads} intra-op threads (the fastest count on this {os.cpu_count()}-thread host)',
-                      'lpips': 'excluded in every arm'},
+                      'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored'},
            'cpu_baseline': {'value': round(val, 6), 'unit': 'steps/s', 'cores': port.threads, 'kind': 'port',
-                            'sample': f'{len(per_step)} bounded samples: per step 1 UNet evaluation + VAE enc/dec + render fwd/bwd on 2048/16384 rays, '
-                                      'scaled to the step (2 renders + n+1 UNet evals + VAE); oracle port (the reference cannot be imported on this box '
+                            'sample': f'{len(per_step)} bounded samples: per step 1 UNet evaluation + VAE enc/dec + LPIPS fwd/bwd + render fwd/bwd on 2048/16384 rays, '
+                                      'scaled to the step (2 renders + n+1 UNet evals + VAE + LPIPS); oracle port (the reference cannot be imported on this box '
                                       'and has no CPU render path)'},
            'e2e': {'value': round(val, 6), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out), flush=True)

@@ -301,6 +301,31 @@ int sfb_upsample2x_render(const float* img, const float* sil, int h, int w, floa
  * resp. 3*H*W elements); g_up [4][H][W] scratch; g_img [h*w,3], g_sil [h*w] outputs. */
 int sfb_fusion_loss(const float* up, const float* target, int H, int W, int mode, float weight, float lambda_color, float lambda_sil,
                     float lambda_opacity, float* sums, float* g_up, int h, int w, float* g_img, float* g_sil, void* stream);
+/* same, with an extra gradient g_extra [3][H][W] w.r.t. the up-sampled colour planes (the perceptual term's, already scaled by its lambda) added
+ * before the adjoint of the bilinear up-sampling */
+int sfb_fusion_loss_ex(const float* up, const float* target, int H, int W, int mode, float weight, float lambda_color, float lambda_sil,
+                       float lambda_opacity, const float* g_extra, float* sums, float* g_up, int h, int w, float* g_img, float* g_sil, void* stream);
+
+/* ==========================================================================================
+ * section 7 -- LPIPS-VGG perceptual term of the fusion loss
+ *    sparsefusion/distillation.py:161, :312-314 -> external/external_utils.py:11-49 -> lpips.LPIPS(net='vgg') (third party, un-vendored:
+ *    algorithm restated in oracle/lpips_oracle.py).  The 13 convolutions and their data-gradient convolutions use sfb_conv2d_nhwc_tf32_ex;
+ *    these are the NHWC fp32 operators around them.  sparsefusion_b200/lpips_vgg.py strings them together (value + gradient w.r.t. pred).
+ * ========================================================================================== */
+/* x [2][H][W][4] <- ((2 v - 1 if normalize) - shift) / scale of pred (image 0) and target (image 1), both [3][H][W] planes; channel 3 = 0 */
+int sfb_lpips_prep(const float* pred, const float* target, int H, int W, int normalize, float* x, void* stream);
+/* g_pred [3][H][W] <- factor * gx[pixel][c] * (2 if normalize) / scale[c]: adjoint of sfb_lpips_prep for image 0 (gx [H][W][4]) */
+int sfb_lpips_prep_backward(const float* gx, int H, int W, int normalize, float factor, float* g_pred, void* stream);
+int sfb_relu_nhwc(float* x, int64_t n, void* stream);
+int sfb_maxpool2x2_nhwc(const float* x, float* y, int NB, int H, int W, int C, void* stream);
+/* one image: gx [H][W][C] <- gy [H/2][W/2][C] routed to the first maximum of each 2x2 window of x (torch semantics), zero where that maximum is
+ * not positive (x is a post-ReLU activation: this is the ReLU mask of the layer below) */
+int sfb_maxpool2x2_relu_backward_nhwc(const float* x, const float* gy, float* gx, int H, int W, int C, void* stream);
+/* g <- (g + g_head) * (act > 0), n floats; g_head may be NULL */
+int sfb_add_relu_mask(float* g, const float* g_head, const float* act, int64_t n, void* stream);
+/* one tap: f0, f1 [HW][C] feature maps of pred / target, w [C] the non-negative 1x1 `lin` weights.  *value += mean_p sum_c w_c (n0 - n1)^2 with
+ * n = f / (||f||_2 + 1e-10) over channels; g_f0 [HW][C] <- d value / d f0 */
+int sfb_lpips_head(const float* f0, const float* f1, const float* w, int HW, int C, float* value, float* g_f0, void* stream);
 
 #ifdef __cplusplus
 }

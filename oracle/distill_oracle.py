@@ -39,7 +39,8 @@ class OracleDistiller:
     """mirrors sparsefusion_b200.distillation.Distiller on CPU tensors; every random draw is injectable"""
 
     def __init__(self, field_params: Dict[str, torch.Tensor], vae, unet_sd, unet_cfg, cache, *, hw_scale=2, z_scale_factor=0.18215,
-                 plms_steps=50, start_fusion_step=1000, seed=0, rank=0, level_scales=None, lr=5e-4):
+                 plms_steps=50, start_fusion_step=1000, seed=0, rank=0, level_scales=None, lr=5e-4, percep=None, lambda_percep=0.1,
+                 start_percep_step=1000):
         self.params = {k: v.clone().requires_grad_(True) for k, v in field_params.items()}
         self.field = no.Field(self.params, level_scales=level_scales)
         self.vae, self.unet_sd, self.cfg, self.cache = vae, unet_sd, unet_cfg, cache
@@ -49,6 +50,7 @@ class OracleDistiller:
         self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=3000, gamma=0.2)
         self.gen = torch.Generator().manual_seed(seed)
         self.rank = rank
+        self.percep, self.lambda_percep, self.start_percep_step = percep, lambda_percep, start_percep_step   # lpips_oracle.PerceptualLoss or None
         self.timing: Dict[str, float] = {}
 
     def _render(self, ro, rd, noise):
@@ -96,6 +98,8 @@ class OracleDistiller:
                 pred_img = unnormalize(self.vae.decode(1.0 / self.z * pred_x0)).clip(0.0, 1.0)
                 t5 = time.perf_counter()
             fusion = ((1 - acp) * (image - pred_img).abs().mean()).sum()
+            if self.percep is not None and itr >= self.start_percep_step:           # distillation.py:176-178, :312-314
+                fusion = fusion + self.percep(image, pred_img, normalize=True).mean() * self.lambda_percep
             self.timing.update(vae_encode=t3 - t2, plms=t4 - t3, vae_decode=t5 - t4)
         else:
             nrgb = c.target_eft_image[vi:vi + 1]

@@ -115,7 +115,8 @@ __global__ void upsample2x_render_kernel(const float* __restrict__ img, const fl
 //                           tmask = (mean_c target > 0.1)                                                  (distillation.py:269-271)
 // g_up [4][H][W] receives d loss / d up; sums[0..2] += (sum colour term, sum silhouette term, sum opacity term).
 __global__ void __launch_bounds__(256) fusion_loss_kernel(const float* __restrict__ up, const float* __restrict__ target, int HW, int mode, float wgt,
-                                                         float lc, float ls, float lo, float* __restrict__ sums, float* __restrict__ g_up) {
+                                                         float lc, float ls, float lo, const float* __restrict__ g_extra, float* __restrict__ sums,
+                                                         float* __restrict__ g_up) {
     __shared__ float sh[8];
     float s_c = 0.f, s_s = 0.f, s_o = 0.f;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
@@ -128,12 +129,13 @@ __global__ void __launch_bounds__(256) fusion_loss_kernel(const float* __restric
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float d = up[(size_t)c * HW + i] - tv[c];
+            const float ge = g_extra != nullptr ? __ldg(g_extra + (size_t)c * HW + i) : 0.f;   // e.g. the perceptual term's gradient
             if (mode == 0) {
                 s_c += fabsf(d);
-                g_up[(size_t)c * HW + i] = wgt * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / (3.f * HW);
+                g_up[(size_t)c * HW + i] = wgt * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / (3.f * HW) + ge;
             } else {
                 s_c += huber_val(d);
-                g_up[(size_t)c * HW + i] = lc * huber_grad(d) / (3.f * HW);
+                g_up[(size_t)c * HW + i] = lc * huber_grad(d) / (3.f * HW) + ge;
             }
         }
         if (mode == 1) {
@@ -210,12 +212,17 @@ int sfb_upsample2x_render(const float* img, const float* sil, int h, int w, floa
 
 int sfb_fusion_loss(const float* up, const float* target, int H, int W, int mode, float weight, float lambda_color, float lambda_sil,
                     float lambda_opacity, float* sums, float* g_up, int h, int w, float* g_img, float* g_sil, void* stream) {
+    return sfb_fusion_loss_ex(up, target, H, W, mode, weight, lambda_color, lambda_sil, lambda_opacity, nullptr, sums, g_up, h, w, g_img, g_sil, stream);
+}
+
+int sfb_fusion_loss_ex(const float* up, const float* target, int H, int W, int mode, float weight, float lambda_color, float lambda_sil,
+                       float lambda_opacity, const float* g_extra, float* sums, float* g_up, int h, int w, float* g_img, float* g_sil, void* stream) {
     SFB_REQUIRE(up && target && sums && g_up && g_img && g_sil, "fusion_loss: null pointer");
     SFB_REQUIRE(H == 2 * h && W == 2 * w && h > 0 && w > 0 && (mode == 0 || mode == 1), "fusion_loss: the full-resolution planes must be 2x the render");
     cudaStream_t st = as_stream(stream);
     SFB_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), st));
     const int blocks = min(ceil_div(H * W, 256), sm_count() * 2);
-    fusion_loss_kernel<<<blocks, 256, 0, st>>>(up, target, H * W, mode, weight, lambda_color, lambda_sil, lambda_opacity, sums, g_up);
+    fusion_loss_kernel<<<blocks, 256, 0, st>>>(up, target, H * W, mode, weight, lambda_color, lambda_sil, lambda_opacity, g_extra, sums, g_up);
     if (int rc = check_launch("fusion_loss(value)")) return rc;
     upsample2x_render_backward_kernel<<<ceil_div(h * w, 256), 256, 0, st>>>(g_up, h, w, g_img, g_sil);
     return check_launch("fusion_loss(adjoint)");

@@ -124,12 +124,14 @@ class FlatAdam:
 class Distiller:
     def __init__(self, ngp, vae, vldm, opt, cache: SceneCache, *, z_scale_factor=0.18215, plms_steps=50, start_fusion_step=1000,
                  lambda_color=1.0, lambda_sil=1.0, lambda_opacity=1e-3, seed=0, rank=0, world_size=1, process_group=None,
-                 use_cuda_graph=True, fused_glue=True):
+                 use_cuda_graph=True, fused_glue=True, percep=None, lambda_percep=0.1, start_percep_step=1000):
         self.ngp, self.vae, self.vldm, self.opt, self.cache = ngp, vae, vldm, opt, cache
         self.z_scale_factor = z_scale_factor
         self.start_fusion_step = start_fusion_step
         self.lambda_color, self.lambda_sil, self.lambda_opacity = lambda_color, lambda_sil, lambda_opacity
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        # perceptual term (distillation.py:161, :176-178, :312-314): a PerceptualLoss module (lpips_vgg.py) or None; lambda switches on at start_percep_step
+        self.percep, self.lambda_percep, self.start_percep_step = percep, lambda_percep, start_percep_step
         self.fused_glue = fused_glue   # image-space losses + their gradients as fused kernels (image_glue.py) instead of ~50 eager launches + autograd
         self.sampler = PLMSSampler(vldm, plms_steps, use_cuda_graph=use_cuda_graph)          # distillation.py:160
         self.optimizer = FlatAdam(ngp, lr=5e-4)                                              # :165-166
@@ -221,6 +223,8 @@ class Distiller:
                 fusion_weight = (1 - alpha_cumprod).to(pred_x0.device)                        # :307
                 pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
             fusion_loss = (fusion_weight * (image - pred_img).abs().mean()).sum()             # :310 ([1]-shaped in the reference)
+            if self.percep is not None and itr >= self.start_percep_step:                     # :176-178, :312-314
+                fusion_loss = fusion_loss + self.percep(image, pred_img, normalize=True).mean() * self.lambda_percep
             self.last['unet_calls'] = self.sampler.last_unet_calls
         else:                                                                                 # EFT bootstrap :316-329
             noisy_rgb = c.target_eft_image[vi:vi + 1]
@@ -247,7 +251,14 @@ class Distiller:
                 pred_x0, _, _, _ = self.sampler.sample(latents, cond_images=feats, use_tqdm=False, return_noise=True, max_thres=max_thres)   # :304
                 pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
             weight = 1.0 - plms_sigmoid(plms_log_snr(float(max_thres)))                      # 1 - alpha_cumprod of the run's first noise level (:307)
-            loss, g_img, g_ws = glue.fusion_loss(up, pred_img[0], hw, hw, 'sds', weight, self.lambda_color, self.lambda_sil, self.lambda_opacity)
+            g_extra, percep_term = None, None
+            if self.percep is not None and itr >= self.start_percep_step:                     # :176-178, :312-314: value and gradient together
+                pv, pg = self.percep.value_and_grad(up[:3], pred_img[0], normalize=True)
+                percep_term, g_extra = pv * self.lambda_percep, pg * self.lambda_percep
+            loss, g_img, g_ws = glue.fusion_loss(up, pred_img[0], hw, hw, 'sds', weight, self.lambda_color, self.lambda_sil, self.lambda_opacity,
+                                                 g_extra=g_extra)
+            if percep_term is not None:
+                loss = loss + percep_term
             self.last['unet_calls'] = self.sampler.last_unet_calls
         else:                                                                                 # EFT bootstrap :316-329
             loss, g_img, g_ws = glue.fusion_loss(up, c.target_eft_image[vi], hw, hw, 'eft', 1.0, self.lambda_color, self.lambda_sil, self.lambda_opacity)

@@ -47,7 +47,7 @@ def upsample2x_render(img: torch.Tensor, sil: torch.Tensor, h: int, w: int) -> t
 
 
 def fusion_loss(up: torch.Tensor, target: torch.Tensor, h: int, w: int, mode: str, weight: float, lambda_color: float, lambda_sil: float,
-                lambda_opacity: float):
+                lambda_opacity: float, g_extra: torch.Tensor = None):
     """distillation.py:310 ('sds': weight * L1 to the decoded image) / :316-329 ('eft': huber to the cached EFT image and its mask), plus the
     opacity term (:336-344).  up = upsample2x_render(...); target [3,2h,2w].  Returns (loss, d loss/d img [h*w,3], d loss/d sil [h*w])."""
     H, W = 2 * h, 2 * w
@@ -56,8 +56,11 @@ def fusion_loss(up: torch.Tensor, target: torch.Tensor, h: int, w: int, mode: st
     g_up = torch.empty_like(up)
     g_img, g_sil = torch.empty(h * w, 3, dtype=torch.float32, device=up.device), torch.empty(h * w, dtype=torch.float32, device=up.device)
     m = {'sds': 0, 'eft': 1}[mode]
-    lib.call('sfb_fusion_loss', lib.fptr(up), lib.fptr(target.contiguous()), H, W, m, float(weight), float(lambda_color), float(lambda_sil),
-             float(lambda_opacity), lib.fptr(sums), lib.fptr(g_up), h, w, lib.fptr(g_img), lib.fptr(g_sil), lib.stream())
+    # g_extra [3,2h,2w]: gradient of further terms w.r.t. the up-sampled colour planes (the perceptual term), joined before the bilinear adjoint
+    assert g_extra is None or tuple(g_extra.shape) == (3, H, W)
+    lib.call('sfb_fusion_loss_ex', lib.fptr(up), lib.fptr(target.contiguous()), H, W, m, float(weight), float(lambda_color), float(lambda_sil),
+             float(lambda_opacity), None if g_extra is None else lib.fptr(g_extra.contiguous()), lib.fptr(sums), lib.fptr(g_up), h, w, lib.fptr(g_img),
+             lib.fptr(g_sil), lib.stream())
     n = H * W
     if m == 0:
         loss = float(weight) * sums[0] / (3.0 * n) + lambda_opacity * sums[2] / n

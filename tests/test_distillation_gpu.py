@@ -14,9 +14,10 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
+@pytest.mark.parametrize('percep', [False, True], ids=['no-lpips', 'lpips'])   # the perceptual term (from iteration 1000 on, distillation.py:176-178)
 @pytest.mark.parametrize('fused_glue', [True, False], ids=['glue-kernels', 'glue-torch'])   # image-space losses: fused kernels / eager torch + autograd
 @pytest.mark.parametrize('itr', [5, 1500])   # EFT bootstrap phase / SDS phase (start_fusion_step = 1000)
-def test_step_matches_restatement(itr, fused_glue):
+def test_step_matches_restatement(itr, fused_glue, percep):
     from _helpers import device_level_scales
     from oracle import distill_oracle as do, ngp_oracle as no, unet_oracle as uo
     from sparsefusion_b200.distillation import Distiller, SceneCache
@@ -37,7 +38,19 @@ def test_step_matches_restatement(itr, fused_glue):
     rng = np.random.default_rng(21)
     noises = {k: (torch.from_numpy(rng.random((N, 64), dtype=np.float32)), torch.from_numpy(rng.random((N, 64), dtype=np.float32))) for k in 'AB'}
     cache_cpu = SceneCache(**scene)
-    ref = do.OracleDistiller(p, vae, sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()))
+    pl_gpu = pl_ref = None
+    if percep:
+        if itr <= 1000:
+            pytest.skip('the perceptual term is off before iteration 1000')
+        from oracle import lpips_oracle as lo
+        from sparsefusion_b200.lpips_vgg import PerceptualLoss, conv_names
+        pl_gpu = PerceptualLoss('vgg', device='cuda', seed=2)
+        psd = pl_gpu.state_dict()
+        pp = {f'conv{i}.weight': psd[n + '.weight'].cpu() for i, n in enumerate(conv_names())}
+        pp.update({f'conv{i}.bias': psd[n + '.bias'].cpu() for i, n in enumerate(conv_names())})
+        pp.update({f'lin{k}.weight': psd[f'lin{k}.model.1.weight'].cpu() for k in range(5)})
+        pl_ref = lo.PerceptualLoss(pp)
+    ref = do.OracleDistiller(p, vae, sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()), percep=pl_ref)
     la_o, lb_o = ref.step(itr, lambda k: noises[k], uo.NoiseSource(seed=5), max_thres=0.13 if itr > 1000 else None)
 
     # ---- GPU
@@ -56,7 +69,7 @@ def test_step_matches_restatement(itr, fused_glue):
                 dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11, fused_glue=fused_glue)
+    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11, fused_glue=fused_glue, percep=pl_gpu)
     src = uo.NoiseSource(seed=5)
     dist.sampler.noise_fn = lambda t: src(t.cpu()).to(t.device)
     dist.render_noise = lambda k: tuple(t.cuda() for t in noises[k])
