@@ -220,3 +220,26 @@ def test_fused_adam_matches_torch():
         opt.step()
         lib.call('sfb_adam_step', lib.fptr(mine), lib.fptr(g), lib.fptr(m), lib.fptr(v), mine.numel(), 5e-3, 0.9, 0.999, 1e-8, step, 1.0, lib.stream())
     assert torch.allclose(mine, ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_baseline_config_c2_view_at_256():
+    """BASELINE configs[1]: render of a random NGP field, views at 256x256 (65 536 rays, chunked 16 384 by render_batched) -- one of the 64
+    fly-around views here: a 4 096-ray subset against the restatement, ray generation through the C-ABI ray kernel, plus the size-independent
+    properties on all rays (opacity in [0,1], colour = opacity-weighted mixture of sigmoid outputs => in [0,1], finite depth inside [near, far])."""
+    from _helpers import device_level_scales as _device_scales
+    from oracle import ngp_oracle as no
+    from sparsefusion_b200 import image_glue as glue
+    net, p, opt = _net(seed=2)
+    net.eval()
+    cam = no.circle_cameras(64)[17]
+    ro, rd = glue.rays_from_camera(torch.from_numpy(cam[0]).cuda(), torch.from_numpy(cam[1]).cuda(), 256, 256, 4.0)
+    with torch.no_grad():
+        out = net.render_batched(ro[None], rd[None], batched=True, bg_color=0, perturb=False, shading='albedo', **dict(vars(opt), max_ray_batch=16384))
+    img, ws, depth = out['image'][0], out['weights_sum'].reshape(-1), out['depth'].reshape(-1)
+    assert img.shape == (65536, 3) and torch.isfinite(img).all() and torch.isfinite(depth).all()
+    assert (ws >= -1e-6).all() and (ws <= 1 + 1e-5).all() and (img >= -1e-6).all() and (img <= 1 + 1e-5).all()
+    sel = torch.from_numpy(np.random.default_rng(0).choice(65536, 4096, replace=False)).cuda()
+    ref = no.run(no.Field(p, level_scales=_device_scales(no.live_geometry())), ro[sel].cpu(), rd[sel].cpu(), training=False)
+    r_img, r_ws = _rel(img[sel], ref['image']), _rel(ws[sel], ref['weights_sum'])
+    print(f'C2 view 256x256: image rel {r_img:.3e}, opacity rel {r_ws:.3e}')
+    assert r_img < 1e-3 and r_ws < 1e-3
