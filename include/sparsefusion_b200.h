@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 1
+#define SFB_ABI_VERSION 2
 
 #define SFB_OK 0
 #define SFB_ERR_ARG 1
