@@ -183,9 +183,12 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 /* nn.SiLU + nn.PixelShuffle(2) of PixelShuffleUpsample (:588-592): y [NB,H,W,4*Co] -> out [NB,2H,2W,ldo] */
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
 /* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
- * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch; counters: NB*G uint32 that are ZERO on entry (the
- * kernel leaves them zero: the statistics are reduced slab-wise across CTAs and the last slab finalises).  Output is TF32-rounded in
- * single-pass mode (it feeds the conv). */
+ * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch (fp64 partial statistics per pixel slab).
+ * counters: at least 2 uint32 that are ZERO before the first call and are then only touched by this function: the batch-1 path is ONE
+ * launch whose <= 128 co-resident CTAs meet at a software grid barrier (counters[0] = arrivals, reset by the last arriver; counters[1] =
+ * generation), so the words are reusable call after call; do not share them between calls that may run concurrently on different
+ * streams.  NULL selects the two-launch path (statistics kernel + apply kernel), which is also what batches > 1 and large images use.
+ * Output is TF32-rounded in single-pass mode (it feeds the conv). */
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
                        int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy,
                        void* stream);

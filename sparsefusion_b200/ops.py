@@ -265,11 +265,17 @@ _GN_COUNTERS = {}
 
 
 def _gn_counters(device, n: int) -> torch.Tensor:
-    """persistent zeroed uint32 counters for the cross-CTA GroupNorm reduction (the kernel leaves them zero)"""
+    """barrier words of the single-launch GroupNorm (zero before first use; the kernel leaves them reusable).  Inside a UNet evaluation every
+    call takes its OWN words from the evaluation's zero arena, so nothing is shared between launches; elsewhere (VAE, stand-alone calls) one
+    persistent set per device serves the calls of the current stream one after the other."""
+    if _arena is not None:
+        t = _arena.take((64,))
+        if t is not None:
+            return t
     key = (device.type, device.index)
     t = _GN_COUNTERS.get(key)
     if t is None or t.numel() < n:
-        t = torch.zeros(max(n, 4096), dtype=torch.int32, device=device)
+        t = torch.zeros(max(n, 64), dtype=torch.int32, device=device)
         _GN_COUNTERS[key] = t
     return t
 
@@ -281,7 +287,7 @@ def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Ten
         out = torch.empty(nb, h, w, c, dtype=torch.float32, device=x.device)
     ldy = _nhwc_meta(out)[4]
     ws = torch.empty(lib.load().sfb_groupnorm_ws_floats(nb, groups), dtype=torch.float32, device=x.device)
-    counters = _gn_counters(x.device, nb * groups)
+    counters = _gn_counters(x.device, 2)
     film_ld = 0
     if film is not None:
         assert film.shape == (nb, 2 * c) and film.stride(1) == 1
