@@ -364,6 +364,16 @@ class Unet(nn.Module):
                 w = P[f'init_conv.convs.{i}.weight']
                 packed[f'init_conv.convs.{i}.weight@cond'] = ops.pack_conv_weight(w[:, :cc].contiguous())
                 packed[f'init_conv.convs.{i}.weight@x'] = ops.pack_conv_weight(w[:, cc:].contiguous())
+        # last down stage: Parallel(conv3x3, conv1x1) summed (:1322) == ONE 3x3 convolution whose centre tap carries the 1x1 weights too
+        for n in list(P):
+            if n.endswith('.4.fns.0.weight') and n.replace('fns.0', 'fns.1') in P:
+                w3, w1 = P[n], P[n.replace('fns.0', 'fns.1')]
+                if w3.shape[2:] == (3, 3) and w1.shape[2:] == (1, 1):
+                    wm = w3.clone()
+                    wm[:, :, 1, 1] += w1[:, :, 0, 0]
+                    base = n[:-len('.fns.0.weight')]
+                    packed[base + '.merged.weight'] = ops.pack_conv_weight(wm)
+                    P[base + '.merged.bias'] = (P[n[:-len('weight')] + 'bias'] + P[n.replace('fns.0', 'fns.1')[:-len('weight')] + 'bias']).contiguous()
         film_names = [n[:-len('.time_mlp.1.weight')] for n in P if n.endswith('.time_mlp.1.weight')]
         film_w = torch.cat([P[f'{b}.time_mlp.1.weight'] for b in film_names], dim=0).contiguous()
         film_b = torch.cat([P[f'{b}.time_mlp.1.bias'] for b in film_names], dim=0).contiguous()
@@ -633,8 +643,11 @@ class Unet(nn.Module):
             if i < n - 1:
                 xcur = self._conv(f'downs.{i}.4', xcur, 4, 2, 1)
             else:  # Parallel(conv3x3, conv1x1) summed (:1322)
-                y = self._conv(f'downs.{i}.4.fns.0', xcur, 3, 1, 1)
-                xcur = self._conv(f'downs.{i}.4.fns.1', xcur, 1, 1, 0, out=y, accumulate=True)
+                if f'downs.{i}.4.merged.weight' in self._plan['packed']:
+                    xcur = self._conv(f'downs.{i}.4.merged', xcur, 3, 1, 1)
+                else:
+                    y = self._conv(f'downs.{i}.4.fns.0', xcur, 3, 1, 1)
+                    xcur = self._conv(f'downs.{i}.4.fns.1', xcur, 1, 1, 0, out=y, accumulate=True)
             if taps is not None:
                 taps[f'downs.{i}.4'] = xcur
 
