@@ -1,6 +1,6 @@
 // conv_tcgen05_v2.cu -- second-generation 3xTF32 implicit-GEMM convolution: the M-side operand goes through TENSOR MEMORY.
 //
-// Why: ncu on round-1's kernel (profiles/) shows the error-compensated path is bound by SHARED-MEMORY bandwidth, not HBM: every
+// Why: ncu on the first kernel of this round (conv_tcgen05.cu, "v1") shows the error-compensated path bound by SHARED-MEMORY bandwidth, not HBM: every
 // stage was read by the splitter, written back twice (hi, lo) and then read six more times by the three MMAs per k-step
 // (~190 KB of smem traffic per 32 KB of operands).  Here:
 //   * the 128-row ("M-side") operand tile lands in smem by TMA once, is read ONCE by the converter warps (thread r owns row r,
@@ -11,6 +11,11 @@
 //     1.60 GB of weights): the WEIGHTS are the M-side operand (128 output channels per CTA, streamed HBM -> smem -> TMEM) and
 //     the pixels the N-side (N = 16/32/64), so the tensor core does no work on padding rows and a stage is 20-32 KB of smem:
 //     6-7 stages = ~100 KB of weights in flight per SM, enough to cover HBM latency at full bandwidth.
+//   * the producer streams the first ring of WEIGHT tiles before griddepcontrol.wait (programmatic dependent launch) on their own arrival
+//     barriers; in swap mode the converter turns them into TMEM operands while the previous kernel is still running;
+//   * launches with more than 64 output pixels (tensor-bound) can take pre-split (hi, lo) weights by TMA (sfb_conv2d_nhwc_tf32_ex), so
+//     the converter only touches the activation tile;
+//   * the swap-mode epilogue transposes the accumulator through the idle stages so that global traffic is 16-byte vectors along channels.
 // D = sum over (tap, channel chunk) of  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (fp32 accumulation in TMEM), as in v1.
 // Tiling, tap -> TMA coordinate mapping, split-K, bias / residual / accumulate epilogue semantics are v1's (conv_tcgen05.cu).
 #include "common.cuh"
