@@ -9,8 +9,9 @@ RNG draws follow the reference line by line (citations inline).  ``INTEGRATION.m
 ``distillation_loop`` calls this.
 
 What runs where: both NGP renders (fused sm_100a kernels, analytic backward), the PLMS sampler's UNet evaluations
-(tcgen05 engine, one CUDA graph replay per evaluation), fused Adam.  The VAE encode/decode are torch modules for now
-(SURVEY.md §8f next row #1); the LPIPS term (:312-314) needs the un-vendored `lpips` package and is not included.
+(tcgen05 engine, one CUDA graph replay per evaluation), the SD VAE encode / decode (``ldm_autoencoder.py``, same engine), the
+image-space losses with their gradients (``image_glue.py``), the LPIPS-VGG term when a ``percep`` module is given (``lpips_vgg.py``;
+:312-314), fused Adam.
 
 Multi-GPU (one process per GPU): sub-step B is sharded over target views -- rank r takes the r-th view of the step's
 permutation -- and the NGP gradients are summed with one all-reduce of the flat 7.46 MB gradient buffer, then every rank
