@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2>&1
-echo "bench exit: $?" >> gpurun_out/bench.log
-tail -2 gpurun_out/bench.log | cut -c1-300; grep -o '"cpu_baseline".*' gpurun_out/bench.log | cut -c1-700
+T=/tmp/prof; mkdir -p $T
+timeout 600 ncu --profile-from-start off --set full --clock-control none -k regex:"gn_grid|gn_apply|gn_stats|gca_|gate_mlp|linear_small|layernorm_rows|mq_attention|cross_attention|concat2|pixel_shuffle" -o $T/simt_full -f python tools/profile_targets.py unet 1 > gpurun_out/prof_simt_full.log 2>&1
+echo "simt_full exit $?"
+ncu -i $T/simt_full.ncu-rep --page raw --csv > gpurun_out/simt_full_raw.csv 2> gpurun_out/simt_full_raw.err
+ls -la $T; wc -l gpurun_out/simt_full_raw.csv
