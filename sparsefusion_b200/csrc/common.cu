@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_set>
+#include <cstdint>
 #include "../../include/sparsefusion_b200.h"
 
 namespace sfb {
@@ -41,21 +42,22 @@ int set_precision_override(int m) { const int old = t_precision_override; t_prec
 void set_precision_mode(int m) { g_precision = m; }
 
 static std::atomic<int> g_carveout{1};
+static inline unsigned long long dev_key(const void* kernel) { return (unsigned long long)(uintptr_t)kernel * 64ull + (unsigned)(current_device() & 63); }
 void prefer_smem(const void* kernel) {
-    static std::unordered_set<const void*> done;
+    static std::unordered_set<unsigned long long> done;     // keyed on (kernel, device): function attributes are per device
     static std::mutex mu;
     if (!g_carveout.load()) return;
     std::lock_guard<std::mutex> lock(mu);
-    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (done.insert(dev_key(kernel)).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 static std::atomic<int> g_pad_smem{0};
 size_t pad_smem(const void* kernel, size_t smem) {
     constexpr size_t kPad = 150 * 1024;
     if (!g_pad_smem.load() || smem >= kPad) return smem;
-    static std::unordered_set<const void*> done;
+    static std::unordered_set<unsigned long long> done;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPad);
+    if (done.insert(dev_key(kernel)).second) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPad);
     return kPad;
 }
 static std::atomic<int> g_pdl{1};
@@ -74,13 +76,20 @@ static std::atomic<int> g_fusion{0x7fffffff};
 int fusion_mask() { return g_fusion.load(); }
 void set_fusion_mask(int m) { g_fusion.store(m); }
 
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
 int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];     // per device ordinal (zero-initialised)
+    const int dev = current_device();
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }

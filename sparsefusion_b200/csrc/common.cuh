@@ -101,8 +101,25 @@ static inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 bloc
 #endif
 
 
-// number of SMs of the current device (cached)
+// number of SMs of the current device (cached per device)
 int sm_count();
+// index of the current CUDA device (cudaGetDevice)
+int current_device();
+
+}  // namespace sfb
+#include <atomic>
+// run `stmt` once per DEVICE (function attributes such as cudaFuncAttributeMaxDynamicSharedMemorySize are per device: a process that
+// touches a second GPU must set them there too).  One bit per device ordinal (mod 64) in a per-site mask.
+#define SFB_ONCE_PER_DEVICE(stmt)                                                         \
+    do {                                                                                  \
+        static std::atomic<unsigned long long> done__{0};                                 \
+        const unsigned long long bit__ = 1ull << (sfb::current_device() & 63);            \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                          \
+            stmt;                                                                         \
+            done__.fetch_or(bit__, std::memory_order_release);                            \
+        }                                                                                 \
+    } while (0)
+namespace sfb {
 
 }  // namespace sfb
 

@@ -308,11 +308,7 @@ int conv_prof_end(cudaStream_t st) {
 
 template <int BN, int NP>
 static int launch_conv(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NP>::kSmemBytes));
-        configured = true;
-    }
+    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NP>::kSmemBytes)));
     conv_prof_begin(st);
     void (*kp)(const ConvGemmParams) = conv_gemm_tf32_kernel<BN, NP>;
     kp<<<grid, kThreads, ConvCfg<BN, NP>::kSmemBytes, st>>>(p);

@@ -374,11 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
 
 template <int BN, bool SWAP>
 static int launch_v2(const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SFB_CUDA(cudaFuncSetAttribute(conv_gemm_v2_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<BN>::kSmemBytes));
-        configured = true;
-    }
+    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(conv_gemm_v2_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<BN>::kSmemBytes)));
     conv_prof_begin(st);
     trace_name(SWAP ? (BN == 16 ? "conv_v2<16,swap>" : BN == 32 ? "conv_v2<32,swap>" : "conv_v2<64,swap>")
                     : (BN == 16 ? "conv_v2<16>" : BN == 32 ? "conv_v2<32>" : BN == 64 ? "conv_v2<64>" : BN == 128 ? "conv_v2<128>" : "conv_v2<256>"));

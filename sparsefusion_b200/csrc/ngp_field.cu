@@ -428,8 +428,7 @@ int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* ra
     SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_forward: give xyz or (rays_o, rays_d, z, T)");
     if (B == 0) return SFB_OK;
     const size_t smem = sizeof(FieldSmem) + (size_t)kHid * kFieldThreads * 4;
-    static bool cfg = false;
-    if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     const uint32_t blocks = min(ceil_div(B, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 3);
     field_forward_kernel<<<blocks, kFieldThreads, smem, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
                                                                             FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, sigma, rgb);
@@ -457,8 +456,7 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
     float* D2 = D1 + (size_t)kHid * Bp;
     float* D3 = D2 + (size_t)kHid * Bp;
     const size_t smem = sizeof(FieldSmemBwd) + (size_t)2 * kHid * kFieldThreads * 4;
-    static bool cfg = false;
-    if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     cudaStream_t st = as_stream(stream);
     const uint32_t blocks = min(ceil_div(Bp, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 2);
     field_backward_kernel<<<blocks, kFieldThreads, smem, st>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, Bp, embeddings, offsets,

@@ -940,14 +940,12 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
     cudaStream_t st = as_stream(stream);
     if (M <= 2) {
         const size_t sm = (size_t)2 * K * 4;
-        static bool cfg = false;
-        if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)); cfg = true; }
+        SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4)));
         SFB_LAUNCH(linear_small_kernel<2>, dim3(ceil_div(O, 8), ceil_div(M, 2)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     } else {
         const size_t sm = (size_t)8 * K * 4;
         SFB_REQUIRE(sm <= 200 * 1024, "linear_small: K too large for 8-row tile");
-        static bool cfg = false;
-        if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+        SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
         SFB_LAUNCH(linear_small_kernel<8>, dim3(ceil_div(O, 8), ceil_div(M, 8)), 256, sm, st, x, ldx, w, bias, res, ldr, y, ldy, M, K, O, pre, post, round_tf32 && precision_mode() == 0);
     }
     return check_launch("linear_small");
@@ -967,8 +965,7 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
     {
         const size_t sm2 = ((size_t)nk * 2 * dh + (size_t)8 * nk) * 4;
         if (dh % 4 == 0 && dh <= 128 && sm2 <= 160 * 1024) {
-            static bool cfg = false;
-            if (!cfg) { SFB_CUDA(cudaFuncSetAttribute(mq_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg = true; }
+            SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(mq_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
             SFB_LAUNCH(mq_attention_smem_kernel, dim3(ceil_div(heads * n, 8), B), 256, sm2, as_stream(stream), q, kv, null_kv, ckv, out, n, heads, dh, nc, scale,
                        (int)(precision_mode() == 0));
             return check_launch("mq_attention");

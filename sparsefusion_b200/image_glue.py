@@ -34,7 +34,8 @@ def photometric_loss(img: torch.Tensor, sil: torch.Tensor, rgb: torch.Tensor, ma
     assert img.shape == (h * w, 3) and sil.numel() == h * w and rgb.shape[-2:] == (h * scale, w * scale)
     sums = torch.empty(3, dtype=torch.float32, device=img.device)
     g_img, g_sil = torch.empty_like(img), torch.empty(h * w, dtype=torch.float32, device=img.device)
-    lib.call('sfb_photometric_loss', lib.fptr(img), lib.fptr(sil), lib.fptr(rgb.contiguous()), lib.fptr(mask.contiguous()), h, w, scale,
+    rgb, mask = rgb.contiguous(), mask.contiguous()     # bound to names: a temporary would be freed (and its block reused) before the launch
+    lib.call('sfb_photometric_loss', lib.fptr(img), lib.fptr(sil), lib.fptr(rgb), lib.fptr(mask), h, w, scale,
              float(lambda_color), float(lambda_sil), float(lambda_opacity), lib.fptr(sums), lib.fptr(g_img), lib.fptr(g_sil), lib.stream())
     return _combine(sums, h * w, lambda_color, lambda_sil, lambda_opacity), g_img, g_sil
 
@@ -58,8 +59,10 @@ def fusion_loss(up: torch.Tensor, target: torch.Tensor, h: int, w: int, mode: st
     m = {'sds': 0, 'eft': 1}[mode]
     # g_extra [3,2h,2w]: gradient of further terms w.r.t. the up-sampled colour planes (the perceptual term), joined before the bilinear adjoint
     assert g_extra is None or tuple(g_extra.shape) == (3, H, W)
-    lib.call('sfb_fusion_loss_ex', lib.fptr(up), lib.fptr(target.contiguous()), H, W, m, float(weight), float(lambda_color), float(lambda_sil),
-             float(lambda_opacity), None if g_extra is None else lib.fptr(g_extra.contiguous()), lib.fptr(sums), lib.fptr(g_up), h, w, lib.fptr(g_img),
+    target = target.contiguous()                         # named: temporaries would be freed before the launch and may alias each other
+    g_extra = None if g_extra is None else g_extra.contiguous()
+    lib.call('sfb_fusion_loss_ex', lib.fptr(up), lib.fptr(target), H, W, m, float(weight), float(lambda_color), float(lambda_sil),
+             float(lambda_opacity), None if g_extra is None else lib.fptr(g_extra), lib.fptr(sums), lib.fptr(g_up), h, w, lib.fptr(g_img),
              lib.fptr(g_sil), lib.stream())
     n = H * W
     if m == 0:

@@ -308,6 +308,11 @@ class AutoencoderKL(nn.Module):
         self._sm100 = None
         return super().load_state_dict(*args, **kwargs)
 
+    def _apply(self, fn, *a, **k):
+        # .to(device) / .float() / .half() move or recast the parameters: the packed copies the engine holds would be stale
+        self._sm100 = None
+        return super()._apply(fn, *a, **k)
+
     def encode(self, x):
         eng = self._engine_for(x)
         if eng is not None:

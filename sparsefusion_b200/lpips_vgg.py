@@ -77,6 +77,10 @@ class PerceptualLoss(nn.Module):
         self._plan = None
         return self
 
+    def _apply(self, fn, *a, **k):
+        self._plan = None           # packed weights follow the parameters (device / dtype moves)
+        return super()._apply(fn, *a, **k)
+
     def _p(self, name: str) -> torch.Tensor:
         return self.get_parameter(name.replace('.', '/'))
 
@@ -117,7 +121,8 @@ class PerceptualLoss(nn.Module):
         st = lib.stream
         with torch.cuda.device(dev):
             x = torch.empty(2, H, W, 4, dtype=torch.float32, device=dev)
-            lib.call('sfb_lpips_prep', lib.fptr(pred.float().contiguous()), lib.fptr(target.float().contiguous()), H, W, int(normalize), lib.fptr(x), st())
+            p32, t32 = pred.float().contiguous(), target.float().contiguous()   # named: two temporaries could share one recycled block
+            lib.call('sfb_lpips_prep', lib.fptr(p32), lib.fptr(t32), H, W, int(normalize), lib.fptr(x), st())
             acts: List[torch.Tensor] = []          # post-ReLU output of every convolution (both images)
             pooled_from: Dict[int, torch.Tensor] = {}
             h, i = x, 0

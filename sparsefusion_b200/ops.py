@@ -228,7 +228,8 @@ def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, c_off: int = 0, round_to_
     nb, c, h, w = src.shape
     dnb, dh, dw, dc, ld = _nhwc_meta(dst)
     assert (dnb, dh, dw) == (nb, h, w) and c_off + c <= dc
-    lib.call('sfb_nchw_to_nhwc', lib.fptr(src.contiguous(), 'src'), dst.data_ptr(), nb, c, h, w, ld, c_off, int(round_to_tf32), lib.stream())
+    src = src.contiguous()
+    lib.call('sfb_nchw_to_nhwc', lib.fptr(src, 'src'), dst.data_ptr(), nb, c, h, w, ld, c_off, int(round_to_tf32), lib.stream())
     return dst
 
 
@@ -328,7 +329,8 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias=None, pre: int = 0, post
 def time_fourier(t: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     b, half = t.shape[0], w.shape[0]
     out = torch.empty(b, 2 * half + 1, dtype=torch.float32, device=t.device)
-    lib.call('sfb_time_fourier', lib.fptr(t.contiguous()), lib.fptr(w), lib.fptr(out), b, half, lib.stream())
+    t = t.contiguous()
+    lib.call('sfb_time_fourier', lib.fptr(t), lib.fptr(w), lib.fptr(out), b, half, lib.stream())
     return out
 
 

@@ -21,12 +21,23 @@ import math
 import torch
 
 from . import _lib as lib
-from .imagen_pytorch import GaussianDiffusionContinuousTimes, UnetGraph
+from .imagen_pytorch import GaussianDiffusionContinuousTimes, UnetGraph, alpha_cosine_log_snr
 
 
 def _log_snr(t: float, s: float = 0.008) -> float:
-    """alpha_cosine_log_snr (external/imagen_pytorch.py:194-196) for a host scalar"""
-    return -math.log(max(math.cos((t + s) / (1 + s) * math.pi * 0.5) ** -2 - 1, 1e-5))
+    """alpha_cosine_log_snr (external/imagen_pytorch.py:194-196) for a host scalar, evaluated with the SAME fp32 torch expression the reference's
+    ``GaussianDiffusionContinuousTimes.log_snr`` runs on its fp32 time tensor.  This matters at t -> 1: cos(pi/2) is 6e-17 in fp64 but -4.4e-8 in
+    fp32, so the fp64 value is -74.7 where the reference conditions the UNet on -33.9 (the ``max_thres >= .99`` branch and ``sample()`` from
+    noise start there).  Everything derived from the log-SNR (alpha, sigma, posterior coefficients) is then computed from this fp32 value."""
+    v = _LOG_SNR_CACHE.get(t)
+    if v is None:
+        if len(_LOG_SNR_CACHE) > 4096:
+            _LOG_SNR_CACHE.clear()
+        v = _LOG_SNR_CACHE[t] = float(alpha_cosine_log_snr(torch.tensor(t, dtype=torch.float32), s))
+    return v
+
+
+_LOG_SNR_CACHE = {}
 
 
 def _sigmoid(x: float) -> float:
@@ -150,9 +161,11 @@ class PLMSSampler:
         def update(x, eps_list, coefs, z, t, t_next):
             alpha, sigma, alpha_next, c, noise_scale = _step_scalars(t, t_next)
             out = torch.empty_like(x)
-            ptrs = [lib.fptr(e.contiguous()) for e in eps_list] + [None] * (4 - len(eps_list))
+            eps_list = [e.contiguous() for e in eps_list]      # held until after the launch
+            z = z.contiguous()
+            ptrs = [lib.fptr(e) for e in eps_list] + [None] * (4 - len(eps_list))
             cf = list(coefs) + [0.0] * (4 - len(coefs))
-            lib.call('sfb_plms_update', lib.fptr(x), *ptrs, *cf, lib.fptr(z.contiguous()), alpha, sigma, alpha_next, c, noise_scale, clip, lib.fptr(out),
+            lib.call('sfb_plms_update', lib.fptr(x), *ptrs, *cf, lib.fptr(z), alpha, sigma, alpha_next, c, noise_scale, clip, lib.fptr(out),
                      None, None, n, st())
             return out
 

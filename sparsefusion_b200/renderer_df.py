@@ -70,8 +70,10 @@ class _RunRender(torch.autograd.Function):
         f = lib.fptr
         g_image = g_image.contiguous() if g_image is not None else torch.zeros(N, 3, device=dev)
         g_sigma, g_rgb = torch.empty(N, 128, device=dev), torch.empty(N, 128, 3, device=dev)
+        g_ws = None if g_ws is None else g_ws.contiguous()
+        g_depth = None if g_depth is None else g_depth.contiguous()
         lib.call('sfb_ray_composite_backward', f(zs), f(sigma), f(rgb), f(nears), f(fars), ctx.bg, N, 128, f(g_image),
-                 None if g_ws is None else f(g_ws.contiguous()), None if g_depth is None else f(g_depth.contiguous()), f(g_sigma), f(g_rgb), st)
+                 None if g_ws is None else f(g_ws), None if g_depth is None else f(g_depth), f(g_sigma), f(g_rgb), st)
         B = N * 128
         tape = torch.empty(lib.load().sfb_ngp_field_tape_floats(B), device=dev)
         g_emb = torch.zeros_like(emb)
