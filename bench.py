@@ -104,7 +104,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------ GPU arm
-def build_gpu(rank, world, device):
+def build_gpu(rank, world, device, views_per_step=None):
     from sparsefusion_b200.distillation import Distiller, SceneCache
     from sparsefusion_b200.imagen_pytorch import Unet
     from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
@@ -127,7 +127,8 @@ def build_gpu(rank, world, device):
     pg = torch.distributed.group.WORLD if world > 1 else None
     from sparsefusion_b200.lpips_vgg import PerceptualLoss
     percep = PerceptualLoss('vgg', device=device, seed=0)                       # distillation.py:161 (random weights: see config.lpips)
-    return Distiller, dict(ngp=ngp, vae=vae, vldm=ddpm, opt=opt), scene, dict(seed=0, rank=rank, world_size=world, process_group=pg, percep=percep)
+    return Distiller, dict(ngp=ngp, vae=vae, vldm=ddpm, opt=opt), scene, dict(seed=0, rank=rank, world_size=world, process_group=pg, percep=percep,
+                                                                            views_per_step=views_per_step)
 
 
 def run_gpu(args):
@@ -142,7 +143,11 @@ def run_gpu(args):
     torch.backends.cuda.matmul.allow_tf32 = True
     from sparsefusion_b200 import _lib, ops
     _lib.load()
-    Distiller, nets, scene, kw = build_gpu(rank, world, device)
+    # step semantics: 1 GPU, no --views: the reference's iteration (one target view, two Adam updates) = BASELINE configs[2].  N GPUs: the view-
+    # batched step of SURVEY §8e with V = N views (one per rank, ONE all-reduce, one Adam update) -- weak scaling over views; --views V fixes V.
+    V = args.views if args.views else (world if world > 1 else None)
+    Distiller, nets, scene, kw = build_gpu(rank, world, device, V)
+    views_per_step = V if V else 1
     K, W = args.steps, args.warmup
     thres = max_thres_sequence(W, K)
 
@@ -189,11 +194,12 @@ def run_gpu(args):
     n_unet = len(unet_events)
     if dist.sampler._graph is not None:
         dist.sampler._graph.timing = None
-    value = world * K / (ms / 1e3)
+    value = views_per_step * K / (ms / 1e3)       # view-steps of the whole job per second (one view per step on one GPU: == steps/s)
 
     # ---- (2) end to end through the public API with HOST buffers: pinned scene cache, per-step H2D of the step's views, D2H of the losses
     e2e_val, h2d, d2h = None, 0, 0
     if not args.no_e2e:
+        from sparsefusion_b200.distillation import shard_views, step_views
         host = scene.pin()
         dist.cache = None
         bytes_per_step = [0]
@@ -202,16 +208,30 @@ def run_gpu(args):
             g = d.gen.get_state()
             n_in, n_t = host.input_rgb.shape[0], host.target_features.shape[0]
             idx = int(torch.randperm(n_in, generator=d.gen)[0])
-            vi = int(torch.randperm(n_t, generator=d.gen)[(1 + d.rank) % n_t])
+            perm = torch.randperm(n_t, generator=d.gen)
             d.gen.set_state(g)    # the step itself redraws the same indices
-            d.cache = _StagedCache(host, device, idx, vi)   # this step's two views: pinned host -> HBM, inside the timed region
+            if d.views_per_step is None:
+                mine, need_in = [int(perm[(1 + d.rank) % n_t])], True
+            else:
+                mine = shard_views(step_views(perm, d.views_per_step), d.rank, d.world_size)
+                need_in = (itr % d.world_size) == d.rank
+            d.cache = _StagedCache(host, device, idx if need_in else None, mine)   # this step's views: pinned host -> HBM, inside the timed region
             bytes_per_step[0] = d.cache.bytes
             a, b = d.step(itr, max_thres=mt)
             return float(a.item()) + float(b.item())   # D2H read of the step's losses (the reference logs loss.item(), :249,:349)
         for i in range(2):
             step_e2e(dist, 1001 + i, thres[i % max(1, W)])
         ms_e2e = timed(dist, step_e2e, K, W)        # same itr numbers and max_thres list as the device-resident leg
-        e2e_val, h2d, d2h = world * K / (ms_e2e / 1e3), bytes_per_step[0], 8
+        e2e_val, h2d, d2h = views_per_step * K / (ms_e2e / 1e3), bytes_per_step[0], 8
+
+    # ---- (2b) BASELINE configs[3] as SURVEY §8d/§8e specify it: a FIXED 64-view minibatch step sharded over the ranks (strong scaling: every rank
+    # distils 64/N views per step as UNet / VAE batches, one all-reduce, one Adam update) -- all ranks take part
+    c4 = None
+    if not args.no_c4:
+        try:
+            c4 = c4_leg(Distiller, nets, scene, kw, device, rank, world, barrier)
+        except Exception as e:   # noqa: BLE001  (the headline line must survive a failure of an auxiliary leg)
+            c4 = {'error': f'{type(e).__name__}: {e}'[:300]}
 
     # ---- (3) roofline of the dominant kernel: instrumented eager UNet evaluations (CUDA events around every conv launch)
     roof = None
@@ -325,158 +345,227 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(float(np.mean(n_calls)) if n_calls else 38.0)
 
+    c2 = gref = None
+    if rank == 0 and world == 1 and not args.no_c2:
+        try:
+            c2 = c2_leg(nets['ngp'], device)
+        except Exception as e:   # noqa: BLE001
+            c2 = {'error': f'{type(e).__name__}: {e}'[:300]}
+    if rank == 0 and world == 1 and not args.no_gpuref:
+        try:
+            gref = gpu_reference_leg(device, float(np.mean(n_calls)) if n_calls else 38.25, ms / K)
+        except Exception as e:   # noqa: BLE001
+            gref = {'error': f'{type(e).__name__}: {e}'[:300]}
+
     if rank == 0:
         out = {'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(value, 4), 'unit': 'steps/s', 'n_gpus': world,
                'steps': K, 'warmup': W, 'ms_per_step': round(ms / K, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f32 (UNet GEMMs: 3xTF32 error-compensated tensor-core passes, fp32 accumulate; NGP: fp32)', 'data': 'synthetic',
-               'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, 7.46 MB NGP-gradient all-reduce per sub-step',
+               'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, ' + ('no collective' if world == 1 else 'ONE 7.46 MB NGP-gradient all-reduce per step'),
                           'unet_evals_per_step_mean': round(float(np.mean(n_calls)), 2) if n_calls else None,
                           'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
                           'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored',
                           'precision_mode': ops.get_precision()},
                'clocks': clk, 'gpu_launches': int(launches),
                'e2e': None if e2e_val is None else {'value': round(e2e_val, 4), 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-               'roofline': roof, 'cpu_baseline': cpu}
+               'roofline': roof, 'cpu_baseline': cpu,
+               # `value` counts view-steps (target views distilled per second over all ranks); a loop iteration (one scene, one parameter update
+               # sequence) takes ms_per_step regardless of N in this weak-scaling default -- both rates are stated
+               'views_per_step': views_per_step, 'views_per_s': round(value, 4), 'optimizer_steps_per_s': round(K / (ms / 1e3), 4),
+               'step_semantics': ('reference iteration: photometric update, then fusion update on ONE target view (distillation.py:244-247,:345-352)' if V is None else
+                                  f'view-batched step (SURVEY 8e): grad(photometric) + mean over {V} target views, {V // world if V >= world else 1} per rank as one UNet/VAE batch, '
+                                  'ONE all-reduce and ONE Adam update per step'),
+               'c4_fixed_views': c4, 'c2_render': c2, 'gpu_reference': gref}
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
 class _StagedCache:
-    """SceneCache view for the end-to-end leg: the step's two views are copied host(pinned) -> device when the step starts"""
+    """SceneCache view for the end-to-end leg: the step's views are copied host(pinned) -> device when the step starts"""
 
-    def __init__(self, host, device, in_idx, tgt_idx):
+    def __init__(self, host, device, in_idx, tgt_views):
         self.bytes = 0
 
-        def stage(t, i):
-            d = t[i:i + 1].to(device, non_blocking=True)
-            self.bytes += d.numel() * d.element_size()
-            return _OneView(d, i, t.shape[0])
-        self.input_rgb, self.input_mask = stage(host.input_rgb, in_idx), stage(host.input_mask, in_idx)
-        self.input_rays_o, self.input_rays_d = stage(host.input_rays_o, in_idx), stage(host.input_rays_d, in_idx)
-        self.target_features = stage(host.target_features, tgt_idx)
-        self.target_rays_o, self.target_rays_d = stage(host.target_rays_o, tgt_idx), stage(host.target_rays_d, tgt_idx)
-        self.target_eft_image = _OneView(None, tgt_idx, host.target_eft_image.shape[0])   # not read in SDS mode
+        def stage(t, idxs):
+            out = {}
+            for i in idxs:
+                d = t[i:i + 1].to(device, non_blocking=True)
+                self.bytes += d.numel() * d.element_size()
+                out[i] = d
+            return _Views(out, t.shape, device)
+        ins = [] if in_idx is None else [in_idx]
+        self.input_rgb, self.input_mask = stage(host.input_rgb, ins), stage(host.input_mask, ins)
+        self.input_rays_o, self.input_rays_d = stage(host.input_rays_o, ins), stage(host.input_rays_d, ins)
+        self.target_features = stage(host.target_features, tgt_views)
+        self.target_rays_o, self.target_rays_d = stage(host.target_rays_o, tgt_views), stage(host.target_rays_d, tgt_views)
+        self.target_eft_image = _Views({}, host.target_eft_image.shape, device)   # not read in SDS mode
 
 
-class _OneView:
-    def __init__(self, data, index, n):
-        self.data, self.index, self.shape = data, index, (n,) + (tuple(data.shape[1:]) if data is not None else ())
-        self.device = data.device if data is not None else None
+class _Views:
+    """the staged rows of one SceneCache field, addressed like the full tensor (t[i], t[i:i+1], t[[i, j, ...]])"""
+
+    def __init__(self, rows, shape, device):
+        self.rows, self.shape, self.device = rows, tuple(shape), device
 
     def __getitem__(self, key):
         if isinstance(key, slice):
-            assert key.start == self.index, 'staged view mismatch'
-            return self.data
-        assert key == self.index, 'staged view mismatch'
-        return self.data[0]
+            assert key.stop == key.start + 1, 'staged view: one-row slices only'
+            return self.rows[key.start]
+        if isinstance(key, (list, tuple)):
+            return torch.cat([self.rows[int(k)] for k in key])
+        return self.rows[int(key)][0]
+
+
+# ------------------------------------------------------------------------------------------------------------------ auxiliary legs
+def c4_leg(Distiller, nets, scene, kw, device, rank, world, barrier, views=64, warmup=2, steps=4):
+    """fixed `views`-view minibatch step over `world` ranks: ms per step, views/s, optimiser steps/s (max over ranks, CUDA events)"""
+    dist = Distiller(cache=scene.to(device), **nets, **dict(kw, views_per_step=views))
+    thres = max_thres_sequence(warmup, steps, seed=4321)
+    for i in range(warmup):
+        dist.step(1001 + i, max_thres=thres[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    calls = []
+    for i in range(steps):
+        dist.step(1001 + warmup + i, max_thres=thres[warmup + i])
+        calls.append(dist.last.get('unet_calls', 0))
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms) / steps
+    per_rank = views // world
+    return {'workload': f'BASELINE configs[3] (SURVEY 8d C4): one optimiser step on a FIXED {views}-view minibatch, views sharded {per_rank} per rank, UNet / VAE batch '
+                        f'{min(per_rank, dist.max_batch)}, per-view RNG keyed by (step, view), one all-reduce per step', 'views': views, 'n_gpus': world,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': round(ms, 2), 'views_per_s': round(views / (ms / 1e3), 3),
+            'optimizer_steps_per_s': round(1e3 / ms, 4), 'unet_evals_per_view_mean': round(float(np.mean(calls)), 2), 'scaling': 'strong'}
+
+
+def c2_leg(ngp, device, n_views=64, hw=256):
+    """BASELINE configs[1]: forward render of the NGP field, 64 views at 256x256, train-mode sampling (perturb + inverse-CDF noise),
+    16 384-ray chunks like render_batched (renderer_df.py:681-718).  FLOPs per sample point: 13.3 k (MLP 12.8 k + interpolation 0.5 k)."""
+    from sparsefusion_b200.synthetic import camera_rays, circle_cameras
+    cams = circle_cameras(n_views)
+    rays = [tuple(torch.from_numpy(a).to(device) for a in camera_rays(c, hw, hw)) for c in cams]
+    ngp.train()
+    out = {}
+    for tag, chunk in (('chunk_16384', 128 * 128), ('whole_view', hw * hw)):
+        kw = dict(batched=True, max_ray_batch=chunk, perturb=True, bg_color=0, ambient_ratio=1.0, shading='albedo', num_steps=64, upsample_steps=64)
+        for ro, rd in rays[:2]:
+            ngp.render_batched(ro[None], rd[None], **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for ro, rd in rays:
+            ngp.render_batched(ro[None], rd[None], **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        n_rays = n_views * hw * hw
+        out[tag] = {'ms': round(ms, 2), 'rays_per_s': round(n_rays / (ms / 1e3), 1), 'fp32_tflops': round(n_rays * 128 * 13.3e3 / (ms / 1e3) / 1e12, 2)}
+    out['workload'] = f'{n_views} views x {hw}x{hw} rays x (64+64) samples, forward only (no_grad), fused run() renderer'
+    out['note'] = ('fully fused render is FP32-SIMT / L2-gather bound, not HBM bound (SURVEY 8d): the meaningful fractions are fp32_tflops against the '
+                   '~80 TFLOP/s FP32 SIMT peak; each point is evaluated once (the reference evaluates the field twice per point)')
+    return out
+
+
+def gpu_reference_leg(device, mean_calls, our_ms_per_step):
+    """the "reference GPU build" comparator: the eager-PyTorch restatement of the reference's step on the SAME GPU -- cuDNN / cuBLAS
+    with TF32 on (what torch 1.11 defaulted to), the reference's own CUDA operators from oracle/_ref where they exist -- timed component by
+    component and assembled into a step (2 renders fwd+bwd + n+1 UNet evaluations + VAE + LPIPS).  A baseline, not the product."""
+    from oracle import gpu_reference
+    r = gpu_reference.time_step_components(device, mean_calls)
+    r['ours_ms_per_step'] = round(our_ms_per_step, 3)
+    r['speedup_vs_gpu_reference'] = round(r['ms_per_step'] / our_ms_per_step, 3)
+    return r
 
 
 # ------------------------------------------------------------------------------------------------------------------ CPU arm
-class CpuPort:
-    """the oracle port of the step's components on all host cores (set up once, sampled per call)"""
-
-    def __init__(self, ray_sample=2048):
-        from oracle import ngp_oracle as no, unet_oracle as uo
-        from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
-        self.no, self.uo, self.cfg = no, uo, uo.FULL
-        self.sd = uo.make_params(self.cfg, seed=0)
-        self.x, self.c = torch.randn(1, 4, 32, 32), torch.randn(1, 256, 32, 32)
-        self.ls = uo.alpha_cosine_log_snr(torch.tensor([0.3]))
-        self.threads = self._pick_threads()
-        self.vae = AutoencoderKL().eval()
-        self.img = torch.rand(1, 3, 256, 256)
-        from oracle import lpips_oracle as lo
-        self.lo, self.lp = lo, lo.make_params(0)
-        self.p = {k: v.clone().requires_grad_(True) for k, v in no.make_field_params(seed=0).items()}
-        ro, rd = no.camera_rays(no.circle_cameras(64)[3], 128, 128)
-        sel = np.random.default_rng(0).choice(ro.shape[0], ray_sample, replace=False)
-        self.ro, self.rd, self.ray_sample = torch.from_numpy(ro[sel]), torch.from_numpy(rd[sel]), ray_sample
-
-    def _pick_threads(self):
-        """the intra-op thread count at which the CPU port is FASTEST on this host.  More is not better: on the 128-thread B200 hosts one batch-1 UNet
-        evaluation takes 27.8 s with 128 threads and 0.26 s with 16 (32x32 feature maps do not feed 128 threads; measured with
-        tools/cpu_threads_probe.py).  Ascending search, stops once a count is 1.5x slower than the best so far."""
-        best, best_t = None, None
-        cands = sorted({n for n in (4, 8, 16, 32, 64, os.cpu_count() or 1) if n <= (os.cpu_count() or 1)})
-        for n in cands:
-            torch.set_num_threads(n)
-            with torch.no_grad():
-                self.uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c)
-                t0 = time.perf_counter()
-                self.uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c)
-                dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best, best_t = n, dt
-            elif dt > 1.5 * best_t:
-                break
-        torch.set_num_threads(best)
-        return best
-
-    def sample(self, with_vae=True):
-        """(seconds per UNet evaluation, per VAE encode+decode, per full-size render fwd+bwd [scaled from the ray sample])"""
-        with torch.no_grad():
-            t0 = time.perf_counter(); self.uo.unet_forward(self.sd, self.cfg, self.x, self.ls, self.c); t_unet = time.perf_counter() - t0
-        t_vae = None
-        if with_vae:   # VAE encode + decode and the perceptual term (forward of both images, backward to the rendered one): input independent costs
-            with torch.no_grad():
-                t0 = time.perf_counter(); z = self.vae.encode(self.img * 2 - 1).mode(); self.vae.decode(z); t_vae = time.perf_counter() - t0
-            a = self.img.clone().requires_grad_(True)
-            t0 = time.perf_counter()
-            self.lo.lpips(self.lp, 2 * a - 1, 2 * self.img.flip(-1) - 1).sum().backward()
-            t_vae += time.perf_counter() - t0
-        for v in self.p.values():
-            v.grad = None
-        n = self.ray_sample
-        t0 = time.perf_counter()
-        r = self.no.run(self.no.Field(self.p), self.ro, self.rd, perturb_noise=torch.rand(n, 64), pdf_noise=torch.rand(n, 64))
-        (r['image'].mean() + r['weights_sum'].mean()).backward()
-        t_render = (time.perf_counter() - t0) * (128 * 128 / n)
-        return t_unet, t_vae, t_render
-
-
 def cpu_baseline(mean_calls):
-    port = CpuPort()
-    samples = [port.sample() for _ in range(3)]
-    t_unet, t_vae, t_render = (min(smp[i] for smp in samples) for i in range(3))
-    step_s = 2 * t_render + mean_calls * t_unet + t_vae
-    return {'value': round(1.0 / step_s, 6), 'unit': 'steps/s', 'cores': port.threads, 'kind': 'port',
-            'sample': f'oracle port on {port.threads} host threads (the fastest count on this {os.cpu_count()}-thread host, searched at start-up), best of 3 '
-                      f'samples: 1 UNet evaluation ({t_unet:.3f} s), VAE encode+decode + LPIPS-VGG fwd/bwd at 256^2 ({t_vae:.3f} s), '
-                      f'render fwd+bwd on 2048 of 16384 rays scaled x8 ({t_render:.3f} s); step = 2 renders + {mean_calls:.1f} UNet evals + VAE + LPIPS '
-                      f'(extrapolated, not run for a whole step). The reference has no CPU path for the NGP render (CUDA-only extensions).'}
+    """rank 0, N == 1: ONE whole step of the oracle port on the host cores at the run's mean PLMS length (plus a 2-evaluation warm-up step)"""
+    port = CpuWholeStep()
+    port.step(1001, 0.013)
+    n = int(round(mean_calls)) - 1
+    dt, tm = port.step(1002, min(0.99, (n + 0.5) / 100.0))
+    return {'value': round(1.0 / dt, 6), 'unit': 'steps/s', 'cores': port.threads, 'kind': 'port',
+            'sample': f'ONE whole step of the oracle port on {port.threads} host threads (fixed count; {os.cpu_count()}-thread host): {dt:.2f} s with {tm["unet_calls"]} FULL-UNet '
+                      f'evaluations ({tm["plms"]:.2f} s), photometric sub-step {tm["substep_a"]:.2f} s, fusion render {tm["render_b"]:.2f} s, VAE {tm.get("vae_encode", 0) + tm.get("vae_decode", 0):.2f} s; '
+                      'nothing sampled or scaled. The reference has no CPU path for the NGP render (CUDA-only extensions).'}
+
+
+REF_THREADS = 16     # intra-op threads of the CPU arm: fixed (a start-up probe picked 16 or 32 from run to run); 16 was the fastest count for the 32x32
+                     # feature maps on the 128-thread B200 hosts (tools/cpu_threads_probe.py: 0.26 s per UNet evaluation vs 27.8 s with 128 threads)
+
+
+class CpuWholeStep:
+    """the reference's iteration restated on the host cores (oracle/distill_oracle.OracleDistiller: FULL UNet, 128x128 rays, 256x256 VAE, LPIPS),
+    run as WHOLE steps -- nothing sampled or scaled"""
+
+    def __init__(self):
+        from oracle import distill_oracle as do, lpips_oracle as lo, ngp_oracle as no, unet_oracle as uo, vae_oracle as vo
+        from sparsefusion_b200.distillation import SceneCache
+        self.threads = max(1, min(REF_THREADS, os.cpu_count() or 1))
+        torch.set_num_threads(self.threads)
+        self.uo = uo
+        cache = SceneCache(**do.synthetic_scene(seed=0))
+        self.n_rays = cache.input_rays_o.shape[1]
+        self.dist = do.OracleDistiller(no.make_field_params(seed=0), vo.TorchVAE(vo.make_params(seed=0)), uo.make_params(uo.FULL, seed=0), uo.FULL, cache,
+                                       seed=0, percep=lo.PerceptualLoss(lo.make_params(0)))
+        self.rng = np.random.default_rng(0)
+
+    def step(self, itr, max_thres):
+        n = self.n_rays
+        noise = lambda k: (torch.from_numpy(self.rng.random((n, 64), dtype=np.float32)), torch.from_numpy(self.rng.random((n, 64), dtype=np.float32)))
+        t0 = time.perf_counter()
+        self.dist.step(itr, noise, self.uo.NoiseSource(seed=itr), max_thres=max_thres)
+        return time.perf_counter() - t0, dict(self.dist.timing)
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the step = the oracle port (the reference cannot be imported on the GPU box and has
+    no CPU render path of its own), whole steps on REF_THREADS host threads.  A whole step takes 10-25 s, so only as many of the K timed steps
+    as fit the time budget are actually run (at least one); the remaining ones are filled in from the measured components of those runs with their
+    own PLMS length (n+1 UNet evaluations) -- the line says how many of each."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
     thres = max_thres_sequence(W, K)
     calls = [min(int(t * 100), 50) + 1 if t >= 0.01 else 0 for t in thres[W:W + K]]
-    per_step = []
-    port = CpuPort()
-    t_vae = None
+    budget = float(os.environ.get('SFB_REF_BUDGET_S', 150))
+    port = CpuWholeStep()
     t_begin = time.perf_counter()
-    for i in range(W + K):
-        t_unet, tv, t_render = port.sample(with_vae=(i < max(W, 1) + 1))   # the VAE cost is input independent: sampled during warm-up + once
-        if tv is not None:
-            t_vae = tv if t_vae is None else min(t_vae, tv)
-        if i >= W:
-            per_step.append(2 * t_render + calls[i - W] * t_unet + t_vae)
-        if time.perf_counter() - t_begin > 240 and len(per_step) >= 1:   # keep the whole run within a few minutes
+    if W > 0:       # one short warm-up step (first-touch allocations, thread pool): 2 UNet evaluations
+        port.step(1000 + 1, 0.013)
+    whole, comps = {}, []
+    for i in range(K):
+        if i > 0 and time.perf_counter() - t_begin > budget:
             break
+        dt, tm = port.step(1001 + W + i, thres[W + i])
+        whole[i] = dt
+        comps.append((tm['total'] - tm['plms'], tm['plms'] / max(1, tm['unet_calls']), tm))
+    fixed = float(np.mean([c[0] for c in comps]))             # everything but the sampler: 2 renders fwd+bwd, VAE, LPIPS, Adam
+    per_call = float(np.mean([c[1] for c in comps if c[2]['unet_calls'] > 0] or [0.0]))
+    per_step = [whole.get(i, fixed + calls[i] * per_call) for i in range(K)]
     step_s = float(np.mean(per_step))
     val = 1.0 / step_s
+    norm = [whole[i] / max(1e-9, fixed + calls[i] * per_call) for i in whole]      # measured / modelled, per whole step: the spread of the measurement
     out = {'impl': 'reference', 'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(val, 6), 'unit': 'steps/s',
            'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': K, 'warmup': W, 'ms_per_step': round(step_s * 1e3, 1), 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': WORKLOAD, 'parallelism': f'host CPU, {port.threads} intra-op threads (the fastest count on this {os.cpu_count()}-thread host)',
+           'config': {'workload': WORKLOAD, 'parallelism': f'host CPU, {port.threads} intra-op threads (fixed; the fastest count measured on the {os.cpu_count()}-thread host class)',
                       'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored'},
+           'whole_steps_measured': len(whole), 'extrapolated_steps': K - len(whole), 'extrapolated': len(whole) < K,
+           'whole_step_s': {'min': round(min(whole.values()), 3), 'max': round(max(whole.values()), 3), 'measured_over_model_min': round(min(norm), 3),
+                            'measured_over_model_max': round(max(norm), 3)},
+           'components_s': {'all_but_sampler': round(fixed, 3), 'per_unet_eval': round(per_call, 4)}, 'wall_s': round(time.perf_counter() - t_begin, 1),
            'cpu_baseline': {'value': round(val, 6), 'unit': 'steps/s', 'cores': port.threads, 'kind': 'port',
-                            'sample': f'{len(per_step)} bounded samples: per step 1 UNet evaluation + VAE enc/dec + LPIPS fwd/bwd + render fwd/bwd on 2048/16384 rays, '
-                                      'scaled to the step (2 renders + n+1 UNet evals + VAE + LPIPS); oracle port (the reference cannot be imported on this box '
-                                      'and has no CPU render path)'},
+                            'sample': f'{len(whole)} WHOLE steps run on the host cores (oracle port: 2 full-size renders fwd+bwd, n+1 FULL-UNet evaluations, VAE '
+                                      f'enc/dec, LPIPS fwd/bwd, Adam), the other {K - len(whole)} of the {K} timed steps filled in from those runs\' measured components '
+                                      'with their own PLMS length; the reference cannot be imported on this box and has no CPU render path'},
            'e2e': {'value': round(val, 6), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out), flush=True)
 
@@ -489,6 +578,10 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', dest='no_e2e', action='store_true')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
+    ap.add_argument('--no-c4', dest='no_c4', action='store_true', help='skip the fixed 64-view minibatch leg')
+    ap.add_argument('--no-c2', dest='no_c2', action='store_true', help='skip the 64-view 256x256 render leg')
+    ap.add_argument('--no-gpuref', dest='no_gpuref', action='store_true', help='skip the eager-PyTorch-on-GPU reference leg')
+    ap.add_argument('--views', type=int, default=0, help='target views per optimiser step (view-batched step); default: 1 on one GPU, N on N GPUs')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     if a.impl == 'reference':

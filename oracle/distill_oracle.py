@@ -6,9 +6,8 @@ TEST INFRASTRUCTURE ONLY.  Used by tests/test_distillation_gpu.py as the checker
 the CPU baseline / `--impl reference` arm (the reference itself has no CPU path for the NGP render -- CUDA-only
 extensions -- and cannot be imported on the GPU box at all).
 
-The VAE is the plain-torch mirror sparsefusion_b200/ldm_autoencoder.py, which oracle/gen_golden.py checks bit-exact
-against the reference's Encoder / Decoder (it is the same sequence of torch.nn modules); it is a leaf dependency with
-no CUDA code, so importing it here does not route the checker through the product's kernels.
+The VAE handed in is oracle/vae_oracle.TorchVAE (torch restatement pinned bit-exact to the reference's Encoder / Decoder by
+tests/golden/vae.npz); the product's AutoencoderKL has no torch / CPU execution path.
 """
 from __future__ import annotations
 

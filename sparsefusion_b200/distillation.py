@@ -13,11 +13,20 @@ What runs where: both NGP renders (fused sm_100a kernels, analytic backward), th
 image-space losses with their gradients (``image_glue.py``), the LPIPS-VGG term when a ``percep`` module is given (``lpips_vgg.py``;
 :312-314), fused Adam.
 
-Multi-GPU (one process per GPU): sub-step B is sharded over target views -- rank r takes the r-th view of the step's
-permutation -- and the NGP gradients are summed with one all-reduce of the flat 7.46 MB gradient buffer, then every rank
-applies the same fused Adam step with grad_scale = 1/world_size.  Sub-step A is replicated (same view, same noise on every
-rank); its gradient goes through the same all-reduce only so that float-atomic ordering cannot let ranks drift apart.
-With world_size == 1 this is exactly the reference's step.
+Two step semantics:
+
+* ``Distiller.step`` with ``views_per_step=None`` on one rank is EXACTLY the reference's iteration: sub-step A, Adam, sub-step B on ONE
+  target view, Adam (distillation.py:244-247, :345-352).
+* ``views_per_step=V`` (BASELINE configs[3]) is the view-batched extension: the photometric sub-step and V target views are
+  evaluated against the SAME parameters, gradient = grad(A) + mean_v grad(B_v), ONE Adam step -- mathematically one optimiser step on a
+  V-view minibatch, not V sequential reference steps.  The V views are entries 1..V of the step's permutation (the reference takes entry 1);
+  rank r distils views ``views[r::R]`` as ONE batch through the VAE and the PLMS sampler (UNet batch = V/R, one shared ``max_thres`` per
+  step, as many renders as views), the photometric sub-step is computed by one rank (``itr % R``), and the flat 7.46 MB gradient is summed
+  with ONE all-reduce per step.  Every random draw of a view (render jitter, inverse-CDF samples, PLMS noise) comes from a generator
+  keyed by (seed, iteration, view), so the step's result does not depend on R (up to fp32 summation order).
+
+``fusion_substep`` / ``photometric_substep`` with world_size > 1 remain as the one-view-per-rank form (rank r takes entry 1 + r of the
+permutation, all-reduce, Adam with grad_scale 1/R) that ``tests/test_multirank_gpu.py`` pins against the single-rank minibatch.
 """
 from __future__ import annotations
 
@@ -49,6 +58,47 @@ def shard_target_view(perm: torch.Tensor, rank: int) -> int:
     """which target view a rank distils this step: entry (1 + rank) of the step's permutation, wrapping (the reference,
     single process, takes entry 1: distillation.py:264).  Ranks < n_targets therefore get distinct views."""
     return int(perm[(1 + rank) % perm.numel()])
+
+
+def step_views(perm: torch.Tensor, views_per_step: int) -> list:
+    """the V target views of a minibatch step: entries 1..V of the step's permutation, wrapping (V = 1 is the reference's choice, :264)"""
+    n = perm.numel()
+    return [int(perm[(1 + j) % n]) for j in range(views_per_step)]
+
+
+def shard_views(views: list, rank: int, world_size: int) -> list:
+    """rank r's share of a step's views: views[r::R] (SURVEY.md §8e: {v : v mod R = r} over the step's list)"""
+    return list(views[rank::world_size])
+
+
+def view_seed(seed: int, itr: int, view: int, stream: int) -> int:
+    """seed of the generator that serves ONE (iteration, view, stream) -- stream 0: photometric render, 1: fusion render, 2: PLMS noise.
+    Keyed draws make a minibatch step independent of how its views are spread over ranks."""
+    x = (seed * 0x9E3779B97F4A7C15 + itr * 0xBF58476D1CE4E5B9 + view * 0x94D049BB133111EB + stream * 0xD6E8FEB86659FD93) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return x & 0x7FFFFFFFFFFFFFFF
+
+
+class KeyedNoise:
+    """``noise_fn`` of the PLMS sampler for a batch of views: row i of every draw comes from view i's own generator (one randn of ``chunk`` draws
+    per view per sampling run, sliced by the sampler's calls), so a view's noise does not depend on which other views share its batch"""
+
+    def __init__(self, seeds, device, chunk: int = 128):
+        self.gens = []
+        for sd in seeds:
+            g = torch.Generator(device=device)
+            g.manual_seed(int(sd))
+            self.gens.append(g)
+        self.device, self.chunk, self.buf, self.pos = device, chunk, None, 0
+
+    def __call__(self, like: torch.Tensor) -> torch.Tensor:
+        assert like.shape[0] == len(self.gens), 'KeyedNoise: batch rows must match the views it was keyed for'
+        if self.buf is None or self.pos >= self.chunk:
+            self.buf = torch.stack([torch.randn(self.chunk, *like.shape[1:], generator=g, device=self.device, dtype=like.dtype) for g in self.gens], dim=1)
+            self.pos = 0
+        out = self.buf[self.pos]
+        self.pos += 1
+        return out
 
 
 @dataclass
@@ -125,12 +175,16 @@ class FlatAdam:
 class Distiller:
     def __init__(self, ngp, vae, vldm, opt, cache: SceneCache, *, z_scale_factor=0.18215, plms_steps=50, start_fusion_step=1000,
                  lambda_color=1.0, lambda_sil=1.0, lambda_opacity=1e-3, seed=0, rank=0, world_size=1, process_group=None,
-                 use_cuda_graph=True, fused_glue=True, percep=None, lambda_percep=0.1, start_percep_step=1000):
+                 use_cuda_graph=True, fused_glue=True, percep=None, lambda_percep=0.1, start_percep_step=1000, views_per_step=None, max_batch=16):
         self.ngp, self.vae, self.vldm, self.opt, self.cache = ngp, vae, vldm, opt, cache
         self.z_scale_factor = z_scale_factor
         self.start_fusion_step = start_fusion_step
         self.lambda_color, self.lambda_sil, self.lambda_opacity = lambda_color, lambda_sil, lambda_opacity
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        # None: the reference's two-update iteration on one view (one rank) / one view per rank (N ranks, legacy form); V: view-batched minibatch step
+        self.views_per_step = views_per_step
+        self.max_batch = max_batch     # views per VAE / PLMS batch on one rank (activations of the VAE decoder: 0.27 GB per tensor per 8 views at 256^2)
+        self.seed = seed
         # perceptual term (distillation.py:161, :176-178, :312-314): a PerceptualLoss module (lpips_vgg.py) or None; lambda switches on at start_percep_step
         self.percep, self.lambda_percep, self.start_percep_step = percep, lambda_percep, start_percep_step
         self.fused_glue = fused_glue   # image-space losses + their gradients as fused kernels (image_glue.py) instead of ~50 eager launches + autograd
@@ -141,6 +195,9 @@ class Distiller:
         self.gen = torch.Generator().manual_seed(seed)
         self.render_kw = dict(staged=False, perturb=True, bg_color=0, ambient_ratio=1.0, shading='albedo', force_all_rays=True, **vars(opt))
         self.render_noise = None   # parity tests: callable('A'|'B') -> (perturb_noise [N,64], pdf_noise [N,64]) replacing torch.rand
+        self.render_noise_keyed = None   # parity tests (minibatch step): callable('A'|'B', view) -> the same pair for that view
+        self.plms_noise = None     # parity tests (minibatch step): callable(views) -> noise_fn for that batch, replacing KeyedNoise
+        self.pred_img_hook = None  # parity tests (minibatch step): callable(views, pred_img) -> pred_img, e.g. to inject a fixed denoised target
         self.last = {}
 
     # ------------------------------------------------------------------------------------------------
@@ -271,6 +328,108 @@ class Distiller:
     def step(self, itr: int, max_thres: Optional[float] = None):
         """one iteration of the reference's main loop (distillation.py:174-352); returns the two losses as device scalars"""
         with torch.cuda.device(self.cache.input_rgb.device):
+            if self.views_per_step is not None:
+                return self.minibatch_step(itr, max_thres)
             a = self.photometric_substep(itr)
             b = self.fusion_substep(itr, max_thres)
         return a, b
+
+    # ------------------------------------------------------------------------------------------------ view-batched step (SURVEY.md §8e)
+    def _keyed_render(self, rays_o, rays_d, itr, view, stream):
+        """render with this (iteration, view)'s own jitter / inverse-CDF draws"""
+        n = rays_o.shape[0]
+        if self.render_noise_keyed is not None:
+            pn, un = self.render_noise_keyed(('A', 'B')[stream], view)
+        else:
+            g = torch.Generator(device=rays_o.device)
+            g.manual_seed(view_seed(self.seed, itr, view, stream))
+            pn = torch.rand(n, self.opt.num_steps, generator=g, device=rays_o.device)            # renderer_df.py:363
+            un = torch.rand(n, self.opt.upsample_steps, generator=g, device=rays_o.device)       # renderer_df.py:31
+        out = self.ngp.render(rays_o[None], rays_d[None], **dict(self.render_kw, perturb_noise=pn, pdf_noise=un))
+        return out['image'].reshape(n, 3), out['weights_sum'].reshape(n), int(round(n ** 0.5))
+
+    def minibatch_step(self, itr: int, max_thres: Optional[float] = None):
+        """one optimiser step on (photometric view + V target views); returns (photometric loss, mean fusion loss) as device scalars.  With
+        world_size R each rank handles views[r::R]; the losses returned are the GLOBAL ones only on the rank(s) that computed every term --
+        use them for logging, not for control flow."""
+        if not self.fused_glue or int(self.opt.hw_scale) != 2:
+            raise NotImplementedError('the view-batched step uses the fused image-space kernels (fused_glue=True, hw_scale=2)')
+        c = self.cache
+        V, R, r = int(self.views_per_step), self.world_size, self.rank
+        dev = c.input_rgb.device
+        n_in, n_t = c.input_rgb.shape[0], c.target_features.shape[0]
+        idx = int(torch.randperm(n_in, generator=self.gen)[0])                                 # :185-186
+        perm = torch.randperm(n_t, generator=self.gen)                                         # :263
+        u = torch.rand(1, generator=self.gen)                                                  # :303: ONE noise level per step, shared by its views
+        views = step_views(perm, V)
+        mine = shard_views(views, r, R)
+        self.ngp.train()
+        self.optimizer.zero_grad()
+        zero = torch.zeros((), device=dev)
+        loss_a = zero
+        # ---- photometric term: one rank (round-robin over iterations), gradient joins the step's single all-reduce
+        if itr % R == r:
+            if self.opt.cuda_ray and itr % 16 == 0:
+                self.ngp.update_extra_state()
+            img, ws, hw = self._keyed_render(c.input_rays_o[idx], c.input_rays_d[idx], itr, idx, 0)
+            loss_a, g_img, g_ws = glue.photometric_loss(img.detach(), ws.detach(), c.input_rgb[idx], c.input_mask[idx], hw, hw, int(self.opt.hw_scale),
+                                                        self.lambda_color, self.lambda_sil, self.lambda_opacity)
+            torch.autograd.backward((img, ws), (g_img, g_ws))
+        elif self.opt.cuda_ray and itr % 16 == 0:
+            self.ngp.update_extra_state()
+        # ---- fusion term over this rank's views, in batches of at most max_batch
+        sds = itr > self.start_fusion_step
+        if sds and max_thres is None:
+            max_thres = u.clamp(min=0.0, max=0.99).item()
+        loss_b = zero
+        calls = 0
+        inv_v = 1.0 / V
+        for lo in range(0, len(mine), self.max_batch):
+            chunk = mine[lo:lo + self.max_batch]
+            renders = [self._keyed_render(c.target_rays_o[v], c.target_rays_d[v], itr, v, 1) for v in chunk]
+            hw = renders[0][2]
+            ups = [glue.upsample2x_render(im.detach(), w.detach(), hw, hw) for im, w, _ in renders]          # :287-288
+            if sds:
+                with torch.no_grad():
+                    batch = torch.stack([up[:3] for up in ups])                                               # [b,3,256,256]
+                    latents = self.vae.encode(normalize(batch)).mode() * self.z_scale_factor                 # :299
+                    feats = c.target_features[chunk] if isinstance(c.target_features, torch.Tensor) else torch.cat([c.target_features[v:v + 1] for v in chunk])
+                    prev_fn = self.sampler.noise_fn
+                    if self.plms_noise is None:
+                        self.sampler.noise_fn = KeyedNoise([view_seed(self.seed, itr, v, 2) for v in chunk], dev)
+                    else:
+                        self.sampler.noise_fn = self.plms_noise(chunk)
+                    try:
+                        pred_x0, _, _, _ = self.sampler.sample(latents, cond_images=feats, use_tqdm=False, return_noise=True, max_thres=max_thres)   # :304
+                    finally:
+                        self.sampler.noise_fn = prev_fn
+                    pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
+                    if self.pred_img_hook is not None:
+                        pred_img = self.pred_img_hook(chunk, pred_img)
+                calls = self.sampler.last_unet_calls
+                weight = 1.0 - plms_sigmoid(plms_log_snr(float(max_thres)))                                  # :307
+            for j, v in enumerate(chunk):
+                im, w, _ = renders[j]
+                if sds:
+                    g_extra, percep_term = None, None
+                    if self.percep is not None and itr >= self.start_percep_step:                             # :176-178, :312-314
+                        pv, pg = self.percep.value_and_grad(ups[j][:3], pred_img[j], normalize=True)
+                        percep_term, g_extra = pv * self.lambda_percep, pg * self.lambda_percep
+                    lv, g_img, g_ws = glue.fusion_loss(ups[j], pred_img[j], hw, hw, 'sds', weight, self.lambda_color, self.lambda_sil,
+                                                       self.lambda_opacity, g_extra=g_extra)
+                    if percep_term is not None:
+                        lv = lv + percep_term
+                else:
+                    lv, g_img, g_ws = glue.fusion_loss(ups[j], c.target_eft_image[v], hw, hw, 'eft', 1.0, self.lambda_color, self.lambda_sil,
+                                                       self.lambda_opacity)
+                torch.autograd.backward((im, w), (g_img * inv_v, g_ws * inv_v))                               # mean over the step's V views
+                loss_b = loss_b + lv * inv_v
+            del renders, ups
+        if sds:
+            self.last['unet_calls'] = calls
+        self.optimizer.sync_grads(R, self.pg)              # the step's ONE collective: sum of every rank's (photometric + fusion) gradient
+        self.optimizer.step(grad_scale=1.0)
+        self.optimizer.scheduler_step()                                                        # :247
+        self.last['photo_loss'], self.last['fusion_loss'] = loss_a, loss_b
+        self.last['views'] = mine
+        return loss_a, loss_b

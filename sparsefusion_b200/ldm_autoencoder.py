@@ -5,32 +5,33 @@ external/ldm/modules/distributions/distributions.py:24-62, config external/ldm/c
 SURVEY.md §8f "next" row #1.  Same module tree and state_dict keys as the reference (``encoder.*``, ``decoder.*``,
 ``quant_conv``, ``post_quant_conv``), without the pytorch_lightning / taming base classes the reference drags in.
 
-Two execution paths behind ``encode`` / ``decode`` (both inference-only in the loop: ``vae.encode(...).mode()`` at
-sparsefusion/distillation.py:299 and ``vae.decode(...)`` at :309 run under no_grad):
-
-* CUDA tensors -> the sm_100a engine (``_Sm100Engine`` below): NHWC activations, every convolution / 1x1 projection / attention
-  matmul on the tcgen05 3xTF32 implicit-GEMM kernel (``ops.conv2d_nhwc``), GroupNorm(32)+swish fused in one pass over the
-  data, nearest upsampling and the row softmax as small kernels.  No cuDNN, no torch matmul.  ``engine='torch'`` restores the
-  plain-torch modules on the GPU for A/B tests.
-* CPU tensors -> the plain torch modules below.  That path exists as the *reference mirror* (tests, bench.py's cpu_baseline);
-  the product path is CUDA and raises if libsparsefusion_b200.so is missing.
+ONE execution path behind ``encode`` / ``decode`` (both inference-only in the loop: ``vae.encode(...).mode()`` at
+sparsefusion/distillation.py:299 and ``vae.decode(...)`` at :309 run under no_grad): the sm_100a engine (``_Sm100Engine`` below) -- NHWC
+activations, every convolution / 1x1 projection / attention matmul on the tcgen05 3xTF32 implicit-GEMM kernel (``ops.conv2d_nhwc``),
+GroupNorm(32)+swish fused in one pass over the data, nearest upsampling and the row softmax as small kernels.  No cuDNN, no torch matmul,
+no CPU fallback: the module classes below are PARAMETER CONTAINERS with the reference's names and shapes (checkpoints load unchanged);
+calling them, or calling encode / decode with non-CUDA tensors, raises.  The plain-torch restatement that checks this engine lives in
+the test oracle's ``vae_oracle`` module (test infrastructure, pinned to the reference's own Encoder / Decoder by tests/golden/vae.npz).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
-
-
-def _swish(x):
-    return x * torch.sigmoid(x)
 
 
 def _norm(c):
     return nn.GroupNorm(num_groups=32, num_channels=c, eps=1e-6, affine=True)
 
 
-class ResnetBlock(nn.Module):
+class _Container(nn.Module):
+    """parameter container: the arithmetic of these blocks runs in _Sm100Engine, never through torch.nn"""
+
+    def forward(self, *a, **k):
+        raise RuntimeError(f'{type(self).__name__} is a parameter container of sparsefusion_b200.AutoencoderKL: the VAE runs on the sm_100a engine '
+                           '(AutoencoderKL.encode / decode with CUDA tensors); there is no torch / CPU execution path')
+
+
+class ResnetBlock(_Container):
     def __init__(self, in_channels, out_channels):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
@@ -41,53 +42,35 @@ class ResnetBlock(nn.Module):
         if in_channels != out_channels:
             self.nin_shortcut = nn.Conv2d(in_channels, out_channels, 1, 1, 0)
 
-    def forward(self, x):
-        h = self.conv1(_swish(self.norm1(x)))
-        h = self.conv2(_swish(self.norm2(h)))
-        if self.in_channels != self.out_channels:
-            x = self.nin_shortcut(x)
-        return x + h
 
 
-class AttnBlock(nn.Module):
+class AttnBlock(_Container):
     def __init__(self, c):
         super().__init__()
         self.norm = _norm(c)
         self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
 
-    def forward(self, x):
-        h = self.norm(x)
-        q, k, v = self.q(h), self.k(h), self.v(h)
-        b, c, hh, ww = q.shape
-        w_ = torch.bmm(q.reshape(b, c, hh * ww).permute(0, 2, 1), k.reshape(b, c, hh * ww)) * (int(c) ** (-0.5))
-        w_ = F.softmax(w_, dim=2)
-        h = torch.bmm(v.reshape(b, c, hh * ww), w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
-        return x + self.proj_out(h)
 
 
-class Downsample(nn.Module):
+class Downsample(_Container):
     def __init__(self, c):
         super().__init__()
         self.conv = nn.Conv2d(c, c, 3, 2, 0)
 
-    def forward(self, x):
-        return self.conv(F.pad(x, (0, 1, 0, 1), mode='constant', value=0))  # asymmetric padding (model.py:73-75)
 
 
-class Upsample(nn.Module):
+class Upsample(_Container):
     def __init__(self, c):
         super().__init__()
         self.conv = nn.Conv2d(c, c, 3, 1, 1)
 
-    def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode='nearest'))
 
 
-class _Level(nn.Module):
+class _Level(_Container):
     pass
 
 
-class Encoder(nn.Module):
+class Encoder(_Container):
     def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, z_channels=4, double_z=True):
         super().__init__()
         self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
@@ -114,18 +97,9 @@ class Encoder(nn.Module):
         self.norm_out = _norm(block_in)
         self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, 1, 1)
 
-    def forward(self, x):
-        h = self.conv_in(x)
-        for i in range(self.num_resolutions):
-            for blk in self.down[i].block:
-                h = blk(h)
-            if i != self.num_resolutions - 1:
-                h = self.down[i].downsample(h)
-        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
-        return self.conv_out(_swish(self.norm_out(h)))
 
 
-class Decoder(nn.Module):
+class Decoder(_Container):
     def __init__(self, ch=128, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4):
         super().__init__()
         self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
@@ -152,15 +126,6 @@ class Decoder(nn.Module):
         self.norm_out = _norm(block_in)
         self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
 
-    def forward(self, z):
-        h = self.conv_in(z)
-        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
-        for i in reversed(range(self.num_resolutions)):
-            for blk in self.up[i].block:
-                h = blk(h)
-            if i != 0:
-                h = self.up[i].upsample(h)
-        return self.conv_out(_swish(self.norm_out(h)))
 
 
 class DiagonalGaussianDistribution:
@@ -278,15 +243,13 @@ class _Sm100Engine:
 
 
 class AutoencoderKL(nn.Module):
-    def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=4, embed_dim=4, engine='sm100'):
+    def __init__(self, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, out_ch=3, z_channels=4, embed_dim=4):
         super().__init__()
         self.encoder = Encoder(ch, ch_mult, num_res_blocks, in_channels, z_channels, True)
         self.decoder = Decoder(ch, out_ch, ch_mult, num_res_blocks, z_channels)
         self.quant_conv = nn.Conv2d(2 * z_channels, 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, z_channels, 1)
         self.embed_dim = embed_dim
-        assert engine in ('sm100', 'torch')
-        self.engine = engine        # CUDA inputs: 'sm100' = the tcgen05 engine, 'torch' = plain torch modules (A/B tests only)
         self._sm100 = None
 
     def prepare(self):
@@ -295,11 +258,11 @@ class AutoencoderKL(nn.Module):
         return self
 
     def _engine_for(self, t):
-        if not t.is_cuda or self.engine != 'sm100':
-            return None
+        if not t.is_cuda:
+            raise RuntimeError('sparsefusion_b200.AutoencoderKL runs on CUDA tensors only (sm_100a engine; there is no CPU fallback)')
         if torch.is_grad_enabled() and (t.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise RuntimeError('the sm_100a VAE engine is inference-only (the distillation loop calls the VAE under no_grad): wrap the call in '
-                               "torch.no_grad() or construct AutoencoderKL(engine='torch')")
+                               'torch.no_grad()')
         if self._sm100 is None:
             self.prepare()
         return self._sm100
@@ -315,17 +278,13 @@ class AutoencoderKL(nn.Module):
 
     def encode(self, x):
         eng = self._engine_for(x)
-        if eng is not None:
-            with torch.no_grad(), torch.cuda.device(x.device):
-                return DiagonalGaussianDistribution(eng.encode_moments(x))
-        return DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
+        with torch.no_grad(), torch.cuda.device(x.device):
+            return DiagonalGaussianDistribution(eng.encode_moments(x))
 
     def decode(self, z):
         eng = self._engine_for(z)
-        if eng is not None:
-            with torch.no_grad(), torch.cuda.device(z.device):
-                return eng.decode(z)
-        return self.decoder(self.post_quant_conv(z))
+        with torch.no_grad(), torch.cuda.device(z.device):
+            return eng.decode(z)
 
     def forward(self, x, sample_posterior=True):
         post = self.encode(x)

@@ -93,7 +93,7 @@ class PLMSSampler:
         batch, device = shape[0], self.diffusion.device
         self.last_unet_calls = 0
         if image is None:
-            image = torch.randn(shape, device=device)
+            image = self.noise_fn(torch.empty(shape, device=device))        # plms.py:73 (torch.randn(shape)); routed through noise_fn for parity tests
         else:
             assert max_thres is not None
         if image.is_cuda and pred_objective == 'noise' and not dynamic_threshold and self.diffusion.clip_output:

@@ -12,20 +12,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.timeout(600)
 def test_reference_arm_prints_the_contract_line():
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'], capture_output=True, text=True,
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', SFB_REF_BUDGET_S='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '0'], capture_output=True, text=True,
                          cwd=ROOT, env=env, timeout=580)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert len(lines) == 1, out.stdout[-2000:]
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'steps/s' and d['higher_is_better'] is True and d['scaling'] == 'weak'
-    assert d['metric'].startswith('distillation-steps/sec') and d['steps'] == 1 and d['n_gpus'] == 1
+    assert d['metric'].startswith('distillation-steps/sec') and d['steps'] == 2 and d['n_gpus'] == 1
     assert d['value'] > 0 and abs(d['ms_per_step'] - 1e3 / d['value']) < 1e-2 * d['ms_per_step']
     assert d['e2e'] == {'value': d['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['value'] == d['value'] and 1 <= cb['cores'] <= (os.cpu_count() or 1) and 'sample' in cb
     assert 'workload' in d['config']
+    # at least one WHOLE step is really run; what is filled in from measured components is declared
+    assert d['whole_steps_measured'] == 1 and d['extrapolated_steps'] == 1 and d['extrapolated'] is True
+    assert d['whole_step_s']['min'] > 0 and d['components_s']['per_unet_eval'] > 0
 
 
 def test_other_ranks_of_the_reference_arm_do_no_work():

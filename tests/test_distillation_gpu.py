@@ -30,6 +30,8 @@ def test_step_matches_restatement(itr, fused_glue, percep):
     scene = do.synthetic_scene(n_input=2, n_target=6, image_size=128, latent=16, feat_ch=cfg.cond_images_channels, render_hw=64, seed=3)
     torch.manual_seed(0)
     vae = AutoencoderKL(ch=32, ch_mult=(1, 2, 4, 4)).eval()
+    from oracle import vae_oracle as vo
+    ref_vae = vo.TorchVAE(vae.state_dict())          # the checker's VAE: torch restatement over the same weights
     sd = uo.make_params(cfg, seed=0)
     p = no.make_field_params(seed=0)
 
@@ -50,7 +52,7 @@ def test_step_matches_restatement(itr, fused_glue, percep):
         pp.update({f'conv{i}.bias': psd[n + '.bias'].cpu() for i, n in enumerate(conv_names())})
         pp.update({f'lin{k}.weight': psd[f'lin{k}.model.1.weight'].cpu() for k in range(5)})
         pl_ref = lo.PerceptualLoss(pp)
-    ref = do.OracleDistiller(p, vae, sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()), percep=pl_ref)
+    ref = do.OracleDistiller(p, ref_vae, sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()), percep=pl_ref)
     la_o, lb_o = ref.step(itr, lambda k: noises[k], uo.NoiseSource(seed=5), max_thres=0.13 if itr > 1000 else None)
 
     # ---- GPU

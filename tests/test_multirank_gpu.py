@@ -25,6 +25,8 @@ def _build(rank, world, pg, device):
     scene = do.synthetic_scene(n_input=2, n_target=6, image_size=128, latent=16, feat_ch=cfg.cond_images_channels, render_hw=64, seed=3)
     torch.manual_seed(0)
     vae = AutoencoderKL(ch=32, ch_mult=(1, 2, 4, 4)).eval()
+    from oracle import vae_oracle as vo
+    ref_vae = vo.TorchVAE(vae.state_dict())          # the checker's VAE: torch restatement over the same weights
     sd = uo.make_params(cfg, seed=0)
     p = no.make_field_params(seed=0)
     opt = get_default_torch_ngp_opt()

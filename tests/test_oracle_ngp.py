@@ -97,3 +97,65 @@ def test_morton_bijection_and_packbits_roundtrip():
     grid = np.random.default_rng(2).standard_normal(4096).astype(np.float32)
     bits = np.unpackbits(no.packbits(grid, 0.1), bitorder='little')
     assert np.array_equal(bits.astype(bool), grid > 0.1)
+
+
+def test_run_restatement_equals_the_references_own_three_pass_run(golden_dir):
+    """ngp_run_ref.npz is the output of the REFERENCE's own NeRFNetwork.run / sample_pdf / MLP / trunc_exp executed on CPU (oracle/gen_golden.py
+    gen_run_ref: renderer_df.py:310-468 with its three field passes :373,:398,:424).  The oracle's run() evaluates the field once at the sorted
+    samples; this test pins that restructuring -- values AND every parameter gradient -- to the literal reference."""
+    from oracle import ngp_oracle as no
+    g, ref = np.load(f'{golden_dir}/ngp_run.npz'), np.load(f'{golden_dir}/ngp_run_ref.npz')
+    N = g['rays_o'].shape[0]
+    pn = torch.from_numpy(np.random.default_rng(int(g['perturb_seed'])).random((N, 64), dtype=np.float32))
+    un = torch.from_numpy(np.random.default_rng(int(g['pdf_seed'])).random((N, 64), dtype=np.float32))
+    params = {k: v.clone().requires_grad_(True) for k, v in no.make_field_params(seed=0).items()}
+    r = no.run(no.Field(params), torch.from_numpy(g['rays_o']), torch.from_numpy(g['rays_d']), perturb_noise=pn, pdf_noise=un)
+    for k in ('image', 'weights_sum', 'depth'):
+        assert np.allclose(r[k].detach().numpy(), ref[k], atol=1e-6), k
+    tgt = torch.from_numpy(np.random.default_rng(int(g['target_seed'])).random((N, 3), dtype=np.float32))
+    loss = ((r['image'] - tgt) ** 2).mean() + 0.1 * r['weights_sum'].mean()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref['loss'])) < 1e-6
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+    for k in no.PARAM_KEYS[1:]:
+        assert rel(params[k].grad.numpy(), ref['g_' + k]) < 1e-5, k
+    gemb = params['encoder.embeddings'].grad.numpy()
+    assert rel(gemb[ref['gemb_rows']], ref['gemb_vals']) < 1e-5
+    assert abs(np.abs(gemb).sum() - float(ref['gemb_abs_sum'])) < 1e-4 * float(ref['gemb_abs_sum'])
+
+
+def test_sample_pdf_equals_the_references(golden_dir):
+    """renderer_df.py:15-49 executed from the reference (stochastic u injected, and det=True) against oracle.sample_pdf"""
+    from oracle import ngp_oracle as no
+    ref = np.load(f'{golden_dir}/ngp_run_ref.npz')
+    rng = np.random.default_rng(int(ref['pdf_seed']))
+    bins = torch.from_numpy(np.sort(rng.random((256, 63), dtype=np.float32) * 4 + 1, axis=1))
+    w = torch.from_numpy(rng.random((256, 62), dtype=np.float32) ** 4)
+    w[:32] = 0
+    u = torch.from_numpy(rng.random((256, 64), dtype=np.float32))
+    assert np.array_equal(no.sample_pdf(bins, w, 64, det=False, u=u).numpy(), ref['pdf_samples'])
+    assert np.array_equal(no.sample_pdf(bins, w, 64, det=True).numpy(), ref['pdf_samples_det'])
+
+
+def test_literal_three_pass_run_of_the_gpu_reference_leg(golden_dir):
+    """oracle/gpu_reference.run_three_pass (what bench.py's eager-GPU baseline times, there with the reference's CUDA operators) restates
+    renderer_df.run literally; with the C stand-ins for the two CUDA operators it reproduces the reference's own output bit for bit on CPU"""
+    from oracle import gpu_reference as gr, ngp_oracle as no
+    g, ref = np.load(f'{golden_dir}/ngp_run.npz'), np.load(f'{golden_dir}/ngp_run_ref.npz')
+    N = g['rays_o'].shape[0]
+    pn = torch.from_numpy(np.random.default_rng(int(g['perturb_seed'])).random((N, 64), dtype=np.float32))
+    un = torch.from_numpy(np.random.default_rng(int(g['pdf_seed'])).random((N, 64), dtype=np.float32))
+    params = {k: v.clone().requires_grad_(True) for k, v in no.make_field_params(seed=0).items()}
+    f = no.Field(params)
+    f.density = lambda x: dict(zip(('sigma', 'albedo'), f.common_forward(x)))
+
+    def nf(ro, rd, aabb, mn):
+        n, fa = no.near_far_from_aabb(ro.numpy(), rd.numpy(), aabb.numpy(), mn)
+        return torch.from_numpy(n), torch.from_numpy(fa)
+    r = gr.run_three_pass(f, torch.from_numpy(g['rays_o']), torch.from_numpy(g['rays_d']), perturb_noise=pn, pdf_noise=un, near_far_fn=nf)
+    for k in ('image', 'weights_sum', 'depth'):
+        assert np.allclose(r[k].detach().numpy(), ref[k], atol=1e-7), k
+    tgt = torch.from_numpy(np.random.default_rng(int(g['target_seed'])).random((N, 3), dtype=np.float32))
+    (((r['image'] - tgt) ** 2).mean() + 0.1 * r['weights_sum'].mean()).backward()
+    for k in no.PARAM_KEYS[1:]:
+        assert np.allclose(params[k].grad.numpy(), ref['g_' + k], rtol=1e-4, atol=1e-8), k

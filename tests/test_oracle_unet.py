@@ -56,10 +56,13 @@ def test_plms_matches_reference_trajectories(golden_dir):
     cfg = uo.SMALL
     sd = uo.make_params(cfg, seed=0)
     x, cond = _inputs(cfg, 1, 3)
-    for max_thres, expect_calls in ((0.004, 0), (0.013, 2), (0.05, 6), (0.21, 22)):
-        key = f'{max_thres:.3f}'
+    # 0.37: 38 calls = the expected run length of a distillation step; 0.99: the `max_thres >= .99` branch (50 steps from t = 1); None: sample() from noise
+    for max_thres, expect_calls in ((0.004, 0), (0.013, 2), (0.05, 6), (0.21, 22), (0.37, 38), (0.99, 51), (None, 51)):
+        key = 'noise' if max_thres is None else f'{max_thres:.3f}'
+        src = uo.NoiseSource(seed=7)
         with torch.no_grad():
-            img, x_noisy, n0, acp, calls = uo.plms_sample(lambda xx, ls: uo.unet_forward(sd, cfg, xx, ls, cond), x, max_thres, uo.NoiseSource(seed=7))
+            start = x if max_thres is not None else src(torch.empty(x.shape))
+            img, x_noisy, n0, acp, calls = uo.plms_sample(lambda xx, ls: uo.unet_forward(sd, cfg, xx, ls, cond), start, .999 if max_thres is None else max_thres, src)
         assert calls == expect_calls == int(g[f'calls_{key}'])
         ref = torch.from_numpy(g[f'img_{key}'])
         assert ((img - ref).norm() / ref.norm()).item() < 1e-4

@@ -100,11 +100,17 @@ def test_plms_sampler_vs_reference_trajectories(golden_dir):
                 dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
     g = np.load(f'{golden_dir}/plms_small.npz')
     x, cond = _inputs(cfg, 1, 3)
-    for max_thres in (0.004, 0.013, 0.05, 0.21):
-        key = f'{max_thres:.3f}'
+    # 0.37 -> 38 UNet calls (a distillation step's expected run); 0.99 -> the `max_thres >= .99` branch from t = 1.0 (fp32 log-SNR -33.9, not the fp64 -74.7);
+    # None -> sample() from noise (plms.py:73, default max_thres .999)
+    for max_thres in (0.004, 0.013, 0.05, 0.21, 0.37, 0.99, None):
+        key = 'noise' if max_thres is None else f'{max_thres:.3f}'
         src = uo.NoiseSource(seed=7)
         sampler = PLMSSampler(ddpm, 50, noise_fn=lambda t: src(t.cpu()).to(t.device))
-        img, x_noisy, noise, acp = sampler.sample(x.cuda(), cond_images=cond.cuda(), use_tqdm=False, return_noise=True, max_thres=max_thres)
+        if max_thres is None:
+            img, x_noisy, noise, acp = sampler.sample(cond_images=cond.cuda(), use_tqdm=False, return_noise=True)
+        else:
+            img, x_noisy, noise, acp = sampler.sample(x.cuda(), cond_images=cond.cuda(), use_tqdm=False, return_noise=True, max_thres=max_thres)
+        assert torch.allclose(acp.cpu(), torch.from_numpy(g[f'acp_{key}']), atol=1e-6)
         assert sampler.last_unet_calls == int(g[f'calls_{key}'])
         rel = _rel(img.cpu(), torch.from_numpy(g[f'img_{key}']))
         print(f'PLMS max_thres={max_thres}: {sampler.last_unet_calls} UNet calls, rel vs reference {rel:.3e}')

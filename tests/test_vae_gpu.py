@@ -1,7 +1,8 @@
-"""SD KL-f8 VAE on the sm_100a engine against the plain-torch mirror of the reference modules in fp64.
+"""SD KL-f8 VAE on the sm_100a engine against (a) the golden vectors minted from the REFERENCE's own Encoder / Decoder
+(tests/golden/vae.npz, oracle/gen_golden.py `vae`) and (b) the torch restatement oracle/vae_oracle.py in fp64 on bigger inputs (tests/test_oracle_vae.py
+pins that restatement to the same golden on CPU).
 
 Bar: relative L2 error <= 1e-3 (BASELINE.json north_star tolerance for floating-point outputs); measured values are printed.
-The fp64 torch modules are the checker here (they are bit-identical mirrors of external/ldm/..., oracle/gen_golden.py vae check).
 """
 import pytest
 import torch
@@ -14,18 +15,32 @@ def _rel(a, b):
 
 
 def _pair(seed=0, **cfg):
+    from oracle import vae_oracle as vo
     from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
-    torch.manual_seed(seed)
-    vae = AutoencoderKL(**cfg).cuda().eval()
-    with torch.no_grad():
-        for n, p in vae.named_parameters():          # non-trivial norms / biases so that every term is exercised
-            if n.endswith('norm1.weight') or n.endswith('norm2.weight') or n.endswith('norm.weight') or n.endswith('norm_out.weight'):
-                p.uniform_(0.5, 1.5)
-            elif n.endswith('.bias'):
-                p.normal_(0, 0.05)
-    ref = AutoencoderKL(engine='torch', **cfg).cuda().double().eval()
-    ref.load_state_dict({k: v.double() for k, v in vae.state_dict().items()})
-    return vae, ref
+    sd = vo.make_params(seed=seed, **cfg)          # non-trivial norm gains / biases so that every term is exercised
+    vae = AutoencoderKL(**cfg)
+    vae.load_state_dict(sd, strict=True)
+    return vae.cuda().eval(), vo.TorchVAE(sd).to('cuda', torch.float64)
+
+
+def test_vae_vs_reference_golden(golden_dir):
+    """outputs of the reference's own modules (fp32, CPU) for the loop's full-width configuration and a narrow one"""
+    import numpy as np
+    g = np.load(f'{golden_dir}/vae.npz')
+    for tag, cfg in (('full', dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2)), ('narrow', dict(ch=32, ch_mult=(1, 2, 4, 4), num_res_blocks=2))):
+        vae, _ = _pair(seed=int(g['param_seed']), **cfg)
+        size = int(g[f'{tag}_size'])
+        rng = np.random.default_rng(int(g['input_seed']))
+        x = torch.from_numpy(rng.random((1, 3, size, size), dtype=np.float32) * 2 - 1).cuda()
+        z = torch.from_numpy(rng.standard_normal((1, 4, size // 8, size // 8), dtype=np.float32)).cuda()
+        with torch.no_grad():
+            post = vae.encode(x)
+            dec = vae.decode(z)
+        mom = torch.from_numpy(g[f'{tag}_moments'])
+        r_mean, r_lv = _rel(post.mean.cpu(), mom[:, :4]), _rel(post.logvar.cpu(), mom[:, 4:].clamp(-30, 20))
+        r_dec = _rel(dec.cpu(), torch.from_numpy(g[f'{tag}_dec']))
+        print(f'{tag}: encode mean rel {r_mean:.3e}, logvar rel {r_lv:.3e}; decode rel {r_dec:.3e} (vs the reference modules)')
+        assert max(r_mean, r_lv, r_dec) < 1e-3
 
 
 @pytest.mark.parametrize('cfg,size', [(dict(ch=128, ch_mult=(1, 2), num_res_blocks=1), 64), (dict(ch=128, ch_mult=(1, 1, 2), num_res_blocks=2), 128)])
@@ -70,6 +85,10 @@ def test_engine_is_inference_only_and_cuda_only():
     x = torch.rand(1, 3, 64, 64, device='cuda')
     with pytest.raises(RuntimeError):
         vae.encode(x)                                   # grad mode on, parameters require grad: refuse instead of silently detaching
+    with pytest.raises(RuntimeError), torch.no_grad():
+        vae.encode(x.cpu())                             # no CPU fallback
+    with pytest.raises(RuntimeError), torch.no_grad():
+        vae.encoder(x)                                  # the module tree holds parameters only; there is no torch execution path
     with torch.no_grad():
         assert vae.encode(x).mode().shape == (1, 4, 32, 32)
 

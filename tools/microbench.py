@@ -233,14 +233,12 @@ def vae_bench(out):
         out['vae_sm100'] = dict(encode_ms=round(timeit(lambda: vae.encode(img).mode(), iters=10, flush=False), 3),
                                 decode_ms=round(timeit(lambda: vae.decode(z), iters=10, flush=False), 3))
         print('vae sm100', out['vae_sm100'], flush=True)
-    vae.engine = 'torch'
+    from oracle import vae_oracle as vo                     # eager torch / cuDNN (TF32) restatement as the comparison
+    tv = vo.TorchVAE(vae.state_dict()).to('cuda')
     with torch.no_grad():
-        enc = timeit(lambda: vae.encode(img).mode(), iters=10, flush=False)
-        dec = timeit(lambda: vae.decode(z), iters=10, flush=False)
-        vcl = vae.to(memory_format=torch.channels_last)
-        imgc = img.contiguous(memory_format=torch.channels_last)
-        enc_cl = timeit(lambda: vcl.encode(imgc).mode(), iters=10, flush=False)
-        dec_cl = timeit(lambda: vcl.decode(z), iters=10, flush=False)
+        enc = timeit(lambda: tv.encode(img).mode(), iters=10, flush=False)
+        dec = timeit(lambda: tv.decode(z), iters=10, flush=False)
+        enc_cl = dec_cl = float('nan')
     out['vae'] = dict(encode_ms=round(enc, 3), decode_ms=round(dec, 3), encode_cl_ms=round(enc_cl, 3), decode_cl_ms=round(dec_cl, 3))
     print('vae', out['vae'], flush=True)
 
