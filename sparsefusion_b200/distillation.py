@@ -308,6 +308,8 @@ class Distiller:
                     max_thres = u.clamp(min=0.0, max=0.99).item()                             # :303
                 pred_x0, _, _, _ = self.sampler.sample(latents, cond_images=feats, use_tqdm=False, return_noise=True, max_thres=max_thres)   # :304
                 pred_img = unnormalize(self.vae.decode(1.0 / self.z_scale_factor * pred_x0)).clip(0.0, 1.0)   # :309
+                if self.pred_img_hook is not None:
+                    pred_img = self.pred_img_hook([vi], pred_img)
             weight = 1.0 - plms_sigmoid(plms_log_snr(float(max_thres)))                      # 1 - alpha_cumprod of the run's first noise level (:307)
             g_extra, percep_term = None, None
             if self.percep is not None and itr >= self.start_percep_step:                     # :176-178, :312-314: value and gradient together
@@ -433,3 +435,113 @@ class Distiller:
         self.last['photo_loss'], self.last['fusion_loss'] = loss_a, loss_b
         self.last['views'] = mine
         return loss_a, loss_b
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# distillation_loop: the reference's entry point (sparsefusion/distillation.py:26-497), same signature
+# ----------------------------------------------------------------------------------------------------------------------
+from .network_grid import NeRFNetwork, get_default_torch_ngp_opt  # noqa: E402,F401  (re-exported: demo.py:9 imports both names from this module)
+
+
+class ReferenceSceneBuilder:
+    """distillation.py:60-127 -- what the reference prepares per scene before its loop: relative / voxel-frame cameras, 50 circle-path
+    augmentation cameras, the 128x128 ray sampler, and the EFT feature cache of every (scene + augmentation) view.  These steps are outside the
+    hot path: they are executed by the REFERENCE's own utilities -- ``utils.camera_utils``, ``utils.render_utils`` (pytorch3d)
+    and the EFT model handed in through ``model_tuple`` -- imported at call time from the reference tree the caller runs in.  The result is the
+    ``SceneCache`` the hot loop consumes: rays as tensors, cached features / low-res EFT images per target view."""
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+
+    def build(self, eft, scene_cameras, scene_rgb, scene_mask, input_idx, use_diffusion=True) -> 'SceneCache':
+        try:
+            from utils.camera_utils import RelativeCameraLoader, get_interpolated_path
+            from utils.render_utils import init_light_field_renderer, init_ray_sampler
+        except ImportError as e:
+            raise RuntimeError('distillation_loop needs the reference tree (utils/camera_utils.py, utils/render_utils.py) and pytorch3d on sys.path to turn '
+                               'pytorch3d cameras into rays and to run the EFT; pass scene_builder=... to supply a SceneCache another way') from e
+        from einops import rearrange
+        gpu = self.gpu
+        relative_cam = RelativeCameraLoader(relative=True, center_at_origin=True)                                    # :65-66
+        relative_cam_no_origin = RelativeCameraLoader(relative=True, center_at_origin=False)
+        scene_cameras_vox = relative_cam_no_origin.get_relative_camera(scene_cameras, query_idx=[0], center_at_origin=False)   # :70
+        scene_cameras_aug = get_interpolated_path(scene_cameras, n=50, method='circle', theta_offset_max=0.17)      # :73
+        scene_cameras_aug = relative_cam.concat_cameras([scene_cameras, scene_cameras_aug])                          # :74
+        scene_cameras_aug_rel = relative_cam.get_relative_camera(scene_cameras_aug, query_idx=[0], center_at_origin=True)      # :75
+        scene_cameras_aug_vox = relative_cam_no_origin.get_relative_camera(scene_cameras_aug, query_idx=[0], center_at_origin=False)
+        blank_rgb = torch.zeros_like(scene_rgb[:1]).repeat(len(scene_cameras_aug), 1, 1, 1)                          # :77-79
+        scene_rgb_aug = torch.cat((scene_rgb, blank_rgb))
+        cam_dist_mean = torch.mean(torch.linalg.norm(scene_cameras.get_camera_center(), axis=1))                     # :82-84
+        min_depth, volume_extent_world = cam_dist_mean - 5.0, cam_dist_mean + 5.0
+        _, _, sampler_feat = init_ray_sampler(gpu, 256, 256, min=min_depth, max=volume_extent_world, scale_factor=2)            # :85
+        _, _, renderer_feat = init_light_field_renderer(gpu, 256, 256, min=min_depth, max=volume_extent_world, scale_factor=8.0)   # :86
+
+        def rays_of(cam):
+            rb = sampler_feat(cam)                                                                                  # :201-204, :274-277
+            return rearrange(rb.origins, 'b h w c -> b (h w) c')[0].contiguous(), rearrange(rb.directions, 'b h w c -> b (h w) c')[0].contiguous()
+        in_o, in_d = zip(*[rays_of(relative_cam.get_camera_slice(scene_cameras_vox, [i])) for i in input_idx])
+        feats, eft_imgs, t_o, t_d = [], [], [], []
+        n_cache = len(scene_cameras_aug_rel) if use_diffusion else 0
+        for ci in range(n_cache):                                                                                   # :95-125
+            q_cam, _, _, input_cameras, input_rgb, _ = relative_cam(scene_cameras_aug_rel, scene_rgb_aug, query_idx=[ci], context_idx=input_idx)
+            eft.encode(input_cameras, input_rgb)
+            with torch.no_grad():
+                epi, _, _ = renderer_feat(cameras=q_cam, volumetric_function=eft.batched_forward, n_batches=16, input_cameras=input_cameras, input_rgb=input_rgb)
+                lr_render, latents = epi.split([3, 256], dim=-1)
+            feats.append(rearrange(latents, 'b h w f -> b f h w'))
+            eft_imgs.append(F.interpolate(rearrange(lr_render, 'b h w f -> b f h w'), scale_factor=8.0, mode='bilinear'))
+            o, d = rays_of(relative_cam.get_camera_slice(scene_cameras_aug_vox, [ci]))
+            t_o.append(o)
+            t_d.append(d)
+        dev = scene_rgb.device
+        n_rays = in_o[0].shape[0]
+        empty = lambda *s: torch.zeros(0, *s, device=dev)
+        return SceneCache(input_rgb=scene_rgb[input_idx].float(), input_mask=scene_mask[input_idx].float(), input_rays_o=torch.stack(in_o), input_rays_d=torch.stack(in_d),
+                          target_features=torch.cat(feats) if feats else empty(256, 32, 32), target_eft_image=torch.cat(eft_imgs) if eft_imgs else empty(3, 256, 256),
+                          target_rays_o=torch.stack(t_o) if t_o else empty(n_rays, 3), target_rays_d=torch.stack(t_d) if t_d else empty(n_rays, 3))
+
+
+def distillation_loop(gpu, args, opt, model_tuple, save_dir, seq_name, scene_cameras, scene_rgb, scene_mask, scene_valid_region, input_idx,
+                      use_diffusion=True, max_itr=3000, loss_fn_vgg=None, *, scene_builder=None, views_per_step=None, on_iteration=None, seed=None,
+                      process_group=None):
+    """sparsefusion/distillation.py:26-497 with the reference's signature (demo.py:87-103 calls it unchanged): builds the per-scene cache
+    (``ReferenceSceneBuilder``, or ``scene_builder.build(...)``), optimises a fresh ``NeRFNetwork(opt)`` for ``max_itr`` iterations with
+    ``Distiller.step`` and saves ``{'model_state_dict': ngp.state_dict()}`` to ``{save_dir}/{seq_name}.pt`` (:495-496).
+
+    Not reproduced: the matplotlib loss plots and the periodic / final visualisation renders, gifs and debug metrics (:355-388, :391-493) -- logging,
+    outside the hot path; ``on_iteration(itr, distiller)`` is the hook for them (``distiller.ngp.render_batched`` is the same call the reference
+    makes).  ``scene_valid_region`` and ``loss_fn_vgg`` are accepted and unused, as in the reference's loop body (:192-195 overwrites the region with
+    ones; loss_fn_vgg only feeds the debug metrics).  Extensions, keyword-only: ``views_per_step`` (view-batched step, see the module docstring; with
+    torch.distributed initialised and ``process_group`` given the views are sharded over its ranks), ``seed``.
+    Returns the optimised network."""
+    import os
+    eft, vae, vldm = model_tuple
+    exp_dir = getattr(args, 'exp_dir', save_dir)
+    os.makedirs(f'{exp_dir}/render_imgs/{seq_name}/', exist_ok=True)                                               # :57-58
+    os.makedirs(f'{exp_dir}/render_gifs/', exist_ok=True)
+    os.makedirs(save_dir, exist_ok=True)
+    device = torch.device('cuda', gpu) if isinstance(gpu, int) else torch.device(gpu)
+    builder = scene_builder if scene_builder is not None else ReferenceSceneBuilder(gpu)
+    cache = builder.build(eft, scene_cameras, scene_rgb, scene_mask, input_idx, use_diffusion=use_diffusion)
+    from .lpips_vgg import PerceptualLoss
+    with torch.cuda.device(device):
+        perceptual_loss = PerceptualLoss('vgg', device=device) if use_diffusion else None                          # :161
+        ngp_network = NeRFNetwork(opt).to(device).train()                                                          # :164
+        rank, world = 0, 1
+        if process_group is not None:
+            rank, world = torch.distributed.get_rank(process_group), torch.distributed.get_world_size(process_group)
+        dist = Distiller(ngp_network, vae, vldm, opt, cache.to(device), plms_steps=50, start_fusion_step=1000, lambda_color=1.0, lambda_sil=1.0,   # :148-160
+                         lambda_opacity=1e-3, seed=torch.seed() % (2 ** 31) if seed is None else seed, rank=rank, world_size=world,
+                         process_group=process_group, percep=perceptual_loss, lambda_percep=0.1, start_percep_step=1000, views_per_step=views_per_step)
+        for itr in range(max_itr):                                                                                  # :174
+            if use_diffusion:
+                dist.step(itr)
+            else:
+                dist.photometric_substep(itr)
+            if on_iteration is not None:
+                on_iteration(itr, dist)
+        torch.cuda.synchronize(device)
+    w_addr = f'{save_dir}/{seq_name}.pt'                                                                            # :495-496
+    torch.save({'model_state_dict': ngp_network.state_dict()}, w_addr)
+    print('input idx', input_idx)
+    return ngp_network

@@ -87,3 +87,106 @@ def test_step_matches_restatement(itr, fused_glue, percep):
         d0 = _rel(ref.params[k].detach(), p[k])
         print(f'    {k:26s} rel diff after 2 Adam steps {r:.3e} (parameter moved by {d0:.3e})')
         assert r < 1e-3 and r < 0.2 * d0 + 1e-6
+
+
+@pytest.mark.timeout(1200)
+def test_c3_sized_step_matches_restatement():
+    """ONE iteration at BASELINE configs[2] size -- FULL UNet (400.7 M parameters), 32x32x4 latents, 256x256 images through the full-width VAE,
+    128x128 rays x (64+64) samples, LPIPS on, max_thres 0.37 -> 38 UNet evaluations (the expected run length) -- against the CPU restatement with
+    every draw injected on both sides.  (The reduced-scene cases above cover both phases and both glue paths; this one covers the size.)"""
+    from _helpers import device_level_scales
+    from oracle import distill_oracle as do, lpips_oracle as lo, ngp_oracle as no, unet_oracle as uo, vae_oracle as vo
+    from sparsefusion_b200.distillation import Distiller, SceneCache
+    from sparsefusion_b200.imagen_pytorch import Unet
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    from sparsefusion_b200.lpips_vgg import PerceptualLoss, conv_names
+    from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
+    from sparsefusion_b200.vldm import DDPM
+    torch.set_num_threads(min(16, torch.get_num_threads()))       # 32x32 feature maps do not feed more threads (tools/cpu_threads_probe.py)
+    cfg = uo.FULL
+    itr, max_thres = 1500, 0.37
+    scene = do.synthetic_scene(n_input=2, n_target=8, seed=3)     # 256^2 images, 32^2 latents, 128^2 rays
+    sd = uo.make_params(cfg, seed=0)
+    vsd = vo.make_params(seed=0)
+    p = no.make_field_params(seed=0)
+    N = 128 * 128
+    rng = np.random.default_rng(21)
+    noises = {k: (torch.from_numpy(rng.random((N, 64), dtype=np.float32)), torch.from_numpy(rng.random((N, 64), dtype=np.float32))) for k in 'AB'}
+    cache_cpu = SceneCache(**scene)
+    pl_gpu = PerceptualLoss('vgg', device='cuda', seed=2)
+    psd = pl_gpu.state_dict()
+    pp = {f'conv{i}.weight': psd[n + '.weight'].cpu() for i, n in enumerate(conv_names())}
+    pp.update({f'conv{i}.bias': psd[n + '.bias'].cpu() for i, n in enumerate(conv_names())})
+    pp.update({f'lin{k}.weight': psd[f'lin{k}.model.1.weight'].cpu() for k in range(5)})
+    ref = do.OracleDistiller(p, vo.TorchVAE(vsd), sd, cfg, cache_cpu, seed=11, level_scales=device_level_scales(no.live_geometry()), percep=lo.PerceptualLoss(pp))
+    la_o, lb_o = ref.step(itr, lambda k: noises[k], uo.NoiseSource(seed=5), max_thres=max_thres)
+
+    opt = get_default_torch_ngp_opt()
+    ngp = NeRFNetwork(opt)
+    st = ngp.state_dict()
+    st.update(p)
+    ngp.load_state_dict(st)
+    ngp = ngp.cuda().train()
+    unet = Unet(channels=cfg.channels, dim=cfg.dim, dim_mults=cfg.dim_mults, num_resnet_blocks=cfg.num_resnet_blocks, layer_attns=cfg.layer_attns,
+                layer_cross_attns=(False,) * 4, cond_images_channels=cfg.cond_images_channels, attn_pool_text=False,
+                attn_dim_head=cfg.attn_dim_head, attn_heads=cfg.attn_heads, cond_on_z=False, conditional_embed_dim=None)
+    unet.load_state_dict(sd)
+    ddpm = DDPM(channels=4, unets=(unet.cuda(),), conditional_encoder=None, conditional_embed_dim=None, image_sizes=(cfg.image_size,), timesteps=500,
+                cond_drop_prob=0.1, pred_objectives='noise', conditional=False, auto_normalize_img=False, clip_output=True,
+                dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
+    vae = AutoencoderKL().eval()
+    vae.load_state_dict(vsd)
+    dist = Distiller(ngp, vae.cuda(), ddpm, opt, cache_cpu.to('cuda'), seed=11, percep=pl_gpu)
+    src = uo.NoiseSource(seed=5)
+    dist.sampler.noise_fn = lambda t: src(t.cpu()).to(t.device)
+    dist.render_noise = lambda k: tuple(t.cuda() for t in noises[k])
+    la, lb = dist.step(itr, max_thres=max_thres)
+    print(f'  C3-sized step: loss A {la.item():.6f} vs {la_o.item():.6f}; loss B {lb.item():.6f} vs {lb_o.item():.6f}; '
+          f'UNet calls {dist.last.get("unet_calls")} vs {ref.timing.get("unet_calls")}; CPU restatement took {ref.timing["total"]:.1f} s')
+    assert dist.last['unet_calls'] == ref.timing['unet_calls'] == 38
+    assert abs(la.item() - la_o.item()) < 1e-3 * abs(la_o.item()) and abs(lb.item() - lb_o.item()) < 1e-3 * abs(lb_o.item())
+    got = dict(ngp.named_parameters())
+    for k in no.PARAM_KEYS:
+        r = _rel(got[k].detach(), ref.params[k].detach())
+        d0 = _rel(ref.params[k].detach(), p[k])
+        print(f'    {k:26s} rel diff after 2 Adam steps {r:.3e} (parameter moved by {d0:.3e})')
+        assert r < 2e-3 and r < 0.2 * d0 + 1e-6
+
+
+def test_distillation_loop_entry_point_with_reference_signature(tmp_path):
+    """sparsefusion/distillation.py:26-41 called the way demo.py:87-103 calls it (positional arguments, the three models as a tuple); the per-scene
+    preprocessing, which needs pytorch3d + the EFT, is supplied through the scene_builder hook; checks the iterations ran and the checkpoint has the
+    reference's layout ({'model_state_dict': ngp.state_dict()}, :495-496)."""
+    from types import SimpleNamespace
+    from oracle import distill_oracle as do, unet_oracle as uo, vae_oracle as vo
+    from sparsefusion_b200.distillation import SceneCache, distillation_loop, get_default_torch_ngp_opt
+    from sparsefusion_b200.imagen_pytorch import Unet
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    from sparsefusion_b200.vldm import DDPM
+    cfg = uo.SMALL
+    scene = do.synthetic_scene(n_input=2, n_target=6, image_size=128, latent=16, feat_ch=cfg.cond_images_channels, render_hw=64, seed=3)
+    vae = AutoencoderKL(ch=32, ch_mult=(1, 2, 4, 4)).eval()
+    vae.load_state_dict(vo.make_params(seed=0, ch=32, ch_mult=(1, 2, 4, 4)))
+    unet = Unet(channels=cfg.channels, dim=cfg.dim, dim_mults=cfg.dim_mults, num_resnet_blocks=cfg.num_resnet_blocks, layer_attns=cfg.layer_attns,
+                layer_cross_attns=(False,) * 4, cond_images_channels=cfg.cond_images_channels, attn_pool_text=False,
+                attn_dim_head=cfg.attn_dim_head, attn_heads=cfg.attn_heads, cond_on_z=False, conditional_embed_dim=None)
+    unet.load_state_dict(uo.make_params(cfg, seed=0))
+    ddpm = DDPM(channels=4, unets=(unet.cuda(),), conditional_encoder=None, conditional_embed_dim=None, image_sizes=(cfg.image_size,), timesteps=500,
+                cond_drop_prob=0.1, pred_objectives='noise', conditional=False, auto_normalize_img=False, clip_output=True,
+                dynamic_thresholding=False, dynamic_thresholding_percentile=.68, clip_value=10).cuda()
+
+    class Builder:
+        def build(self, eft, scene_cameras, scene_rgb, scene_mask, input_idx, use_diffusion=True):
+            assert eft == 'eft-model' and input_idx == [0, 1]
+            return SceneCache(**scene)
+    seen = []
+    args = SimpleNamespace(exp_dir=str(tmp_path / 'exp'), category='hydrant')
+    opt = get_default_torch_ngp_opt()
+    net = distillation_loop(0, args, opt, ('eft-model', vae.cuda(), ddpm), str(tmp_path / 'out'), 'hydrant_000_c2', None, scene['input_rgb'], scene['input_mask'],
+                            None, [0, 1], use_diffusion=True, max_itr=3, loss_fn_vgg=None, scene_builder=Builder(), seed=5,
+                            on_iteration=lambda itr, d: seen.append((itr, float(d.last['photo_loss']), float(d.last['fusion_loss']))))
+    assert [s[0] for s in seen] == [0, 1, 2] and all(np.isfinite(s[1]) and np.isfinite(s[2]) for s in seen)
+    ck = torch.load(str(tmp_path / 'out' / 'hydrant_000_c2.pt'), map_location='cpu')
+    sd = ck['model_state_dict']
+    assert set(sd) == set(net.state_dict()) and sd['encoder.embeddings'].shape == (929336, 2)
+    assert sd['encoder.embeddings'].abs().max() > 1e-4                      # the grid moved away from its +-1e-4 initialisation (3 x 2 Adam updates at lr 5e-3)

@@ -49,6 +49,14 @@ def _build(rank, world, pg, device):
     dist.render_noise = lambda k: noise
     src = uo.NoiseSource(seed=50 + rank)
     dist.sampler.noise_fn = lambda t: src(t.cpu()).to(t.device)
+    # SDS phase: the loss is an L1 against the decoded PLMS sample, and that sample differs at 1e-6 between any two runs (split-K reduction order
+    # of the UNet), which flips sign(image - pred) on near-tie pixels.  The denoised target is therefore replaced on both sides by a fixed image per
+    # view (the sampler and the VAE still run; their output is checked in tests/test_distillation_gpu.py): what is compared here is the sharding,
+    # the collective and the update, deterministically.
+    def fixed_target(views, pred_img):
+        g = torch.Generator().manual_seed(1000 + views[0])
+        return torch.rand(pred_img.shape, generator=g).to(pred_img.device)
+    dist.pred_img_hook = fixed_target
     return dist
 
 
@@ -66,11 +74,10 @@ def _worker(rank, world, store, out_dir, itr):
         td.destroy_process_group()
 
 
-# itr 5: EFT-bootstrap loss (smooth huber, no UNet) -> everything but the float atomics of the grid backward is deterministic: tight bound.
-# itr 1500: SDS loss = L1 against the decoded PLMS sample; the split-K reductions of the UNet make that sample differ at 1e-6 between two
-# runs, which flips sign(image - pred) on a few near-tie pixels -> the gradient comparison is necessarily looser there.
+# itr 5: EFT-bootstrap loss (smooth huber, no UNet); itr 1500: SDS loss with the denoised target injected on both sides (see _build) -> in both
+# cases everything but the float atomics of the grid backward is deterministic: tight bounds.
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('itr,tol', [(5, 1e-4), (1500, 0.25)])   # measured: 1e-7 (smooth loss); 3e-3 .. 3e-2 (L1 sign flips between two runs)
+@pytest.mark.parametrize('itr,tol', [(5, 1e-4), (1500, 1e-3)])
 def test_two_rank_fusion_step_equals_two_view_minibatch(itr, tol):
     import torch.multiprocessing as mp
     world = 2
