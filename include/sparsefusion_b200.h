@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 2
+#define SFB_ABI_VERSION 3
 
 #define SFB_OK 0
 #define SFB_ERR_ARG 1
@@ -215,6 +215,12 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
  * Sigmoid, :929-933), out = h * gate + res.  hid [NB][Hd], w2 [C][Hd]. */
 int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, const float* w2, const float* b2, int Hd, const float* res, int64_t ldr,
                                float* out, int64_t ldo, int NB, int HW, int C, void* stream);
+/* GlobalContext + ResnetBlock tail as ONE launch (imagen_pytorch.py:919-941, :727-729): out = h * Sigmoid(net.2 SiLU(net.0 pool(h))) + res with
+ * pool(h) = sum_p softmax_p(to_k(h)) h[p].  wk [C], bk [1], w0 [Hd][C], b0 [Hd], w2 [C][Hd], b2 [C].  One thread-block cluster per image keeps h in
+ * shared memory; returns SFB_ERR_UNSUPPORTED (no message) when an image's slab does not fit -- callers then use sfb_gca_pool + sfb_linear_small +
+ * sfb_gate_mlp_residual_nhwc. */
+int sfb_gca_tail_nhwc(const float* h, int64_t ldh, const float* wk, const float* bk, const float* w0, const float* b0, const float* w2,
+                      const float* b2, int Hd, const float* res, int64_t ldr, float* out, int64_t ldo, int NB, int HW, int C, void* stream);
 /* VAE helpers.  softmax over the columns of every row of scale * x (ldm AttnBlock, model.py:183-190);
  * nearest-neighbour x2 upsampling in NHWC (ldm Upsample, model.py:44-52). */
 int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream);

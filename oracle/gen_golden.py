@@ -46,9 +46,15 @@ def _reference_unet(cfg, sd):
     return unet.eval()
 
 
-def gen_unet():
+def gen_unet(only=()):
     from oracle import unet_oracle as uo
-    for tag, cfg, batch in (('small', uo.SMALL, 2), ('full', uo.FULL, 1)):
+    import dataclasses
+    # small128: BASELINE configs[4] geometry (128x128x4 latents: 16x16 = 256 tokens + 2 time tokens + null key at the attention stage, 16 384-pixel
+    # convolutions) at the narrow width, so that the reference itself can mint it on CPU
+    which = [('small', uo.SMALL, 2), ('full', uo.FULL, 1), ('small128', dataclasses.replace(uo.SMALL, image_size=128), 1)]
+    if only:
+        which = [w for w in which if w[0] in only]
+    for tag, cfg, batch in which:
         sd = uo.make_params(cfg, seed=0)
         unet = _reference_unet(cfg, sd)
         assert set(unet.state_dict().keys()) == set(sd.keys())
@@ -63,7 +69,8 @@ def gen_unet():
         assert rel < 1e-5
         keep = {k: v.numpy() for k, v in taps.items() if k in ('init_conv', 't', 'c', 'downs.0.1', 'downs.3.3', 'mid_attn', 'ups.0.2', 'ups.0.3', 'final_res_block')}
         np.savez_compressed(os.path.join(GOLD, f'unet_{tag}.npz'), eps=eps.numpy(), t=t.numpy(), batch=batch, seed_inputs=1,
-                            seed_params=0, **({f'tap_{k}': v for k, v in keep.items()} if tag == 'small' else {}))
+                            seed_params=0, **({f'tap_{k}': v for k, v in keep.items()} if tag == 'small' else
+                                              {f'tap_{k}': v for k, v in keep.items() if k in ('mid_attn', 'downs.3.3')} if tag == 'small128' else {}))
 
 
 def gen_plms():
@@ -281,6 +288,8 @@ if __name__ == '__main__':
     torch.set_num_threads(os.cpu_count())
     if 'unet' in which:
         gen_unet()
+    if 'unet128' in which:
+        gen_unet(only=('small128',))
     if 'plms' in which:
         gen_plms()
     if 'ngp' in which:

@@ -50,8 +50,8 @@ def make_params(seed: int = 0) -> Dict[str, torch.Tensor]:
 
 def features(p: Dict[str, torch.Tensor], x: torch.Tensor) -> List[torch.Tensor]:
     """x [B,3,H,W] in [-1,1] -> the five tapped feature maps"""
-    shift = torch.tensor(SHIFT, dtype=x.dtype).view(1, 3, 1, 1)
-    scale = torch.tensor(SCALE, dtype=x.dtype).view(1, 3, 1, 1)
+    shift = torch.tensor(SHIFT, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    scale = torch.tensor(SCALE, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     h = (x - shift) / scale
     outs, i = [], 0
     for v in CFG:

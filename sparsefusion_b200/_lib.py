@@ -68,7 +68,7 @@ def load() -> ctypes.CDLL:
         fn.argtypes = [_argtype(a) for a in args]
         fn.restype = {'void': None, 'int': ctypes.c_int, 'uint32_t': ctypes.c_uint32, 'uint64_t': ctypes.c_uint64,
                       'int64_t': ctypes.c_int64}.get(ret, ctypes.c_char_p if 'char' in ret else ctypes.c_int)
-    if lib.sfb_abi_version() != 2:
+    if lib.sfb_abi_version() != 3:
         raise RuntimeError('libsparsefusion_b200.so ABI version mismatch')
     _lib = lib
     return lib

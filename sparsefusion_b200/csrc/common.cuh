@@ -43,7 +43,9 @@ void phase_bind_conv_v2(unsigned long long* buf, unsigned int cap);
 // optional paths (sfb_set_fusion): bit 0 = NGP MLP weight gradients as tcgen05 GEMMs (off: the SIMT outer-product kernel)
 int fusion_mask();
 static inline bool wgrad_tc_enabled() { return (fusion_mask() & 1) != 0; }
-static inline bool gn_grid_enabled() { return (fusion_mask() & 2) != 0; }   // single-launch GroupNorm with a software grid barrier (batch 1)
+static inline bool gn_grid_enabled() { return (fusion_mask() & 2) != 0; }
+static inline bool gn_cluster_enabled() { return (fusion_mask() & 4) != 0; }   // single-launch GroupNorm: one thread-block cluster per (image, group)
+static inline bool gca_cluster_enabled() { return (fusion_mask() & 8) != 0; }  // GlobalContext + gate + residual as one cluster kernel   // single-launch GroupNorm with a software grid barrier (batch 1)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

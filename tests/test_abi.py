@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
 def test_load_sets_signatures_and_reports_errors():
     from sparsefusion_b200 import _lib
     lib = _lib.load()
-    assert lib.sfb_abi_version() == 2
+    assert lib.sfb_abi_version() == 3
     # argument validation happens before any CUDA call, so it is testable without a GPU
     with pytest.raises(RuntimeError, match='null pointer'):
         _lib.call('sfb_near_far_from_aabb', None, None, None, 4, 0.1, None, None, None)

@@ -37,6 +37,22 @@ def test_small_unet_matches_reference_golden(golden_dir):
             assert ((taps[k[4:]] - t).norm() / t.norm()).item() < 1e-5, k
 
 
+def test_unet_at_128x128_latents_matches_reference_golden(golden_dir):
+    """BASELINE configs[4] geometry: 128x128x4 latents (256 queries x 259 keys at the attention stage), narrow width"""
+    import dataclasses
+    from oracle import unet_oracle as uo
+    cfg = dataclasses.replace(uo.SMALL, image_size=128)
+    g = np.load(f'{golden_dir}/unet_small128.npz')
+    sd = uo.make_params(cfg, seed=int(g['seed_params']))
+    x, cond = _inputs(cfg, int(g['batch']), int(g['seed_inputs']))
+    taps = {}
+    with torch.no_grad():
+        eps = uo.unet_forward(sd, cfg, x, uo.alpha_cosine_log_snr(torch.from_numpy(g['t'])), cond, taps)
+    ref = torch.from_numpy(g['eps'])
+    assert ((eps - ref).norm() / ref.norm()).item() < 1e-5 and tuple(taps['mid_attn'].shape[-2:]) == (16, 16)
+    assert ((taps['mid_attn'] - torch.from_numpy(g['tap_mid_attn'])).norm() / torch.from_numpy(g['tap_mid_attn']).norm()).item() < 1e-5
+
+
 @pytest.mark.timeout(600)
 def test_full_unet_matches_reference_golden(golden_dir):
     from oracle import unet_oracle as uo
