@@ -215,12 +215,6 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
  * Sigmoid, :929-933), out = h * gate + res.  hid [NB][Hd], w2 [C][Hd]. */
 int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, const float* w2, const float* b2, int Hd, const float* res, int64_t ldr,
                                float* out, int64_t ldo, int NB, int HW, int C, void* stream);
-/* GlobalContext + ResnetBlock tail as ONE launch (imagen_pytorch.py:919-941, :727-729): out = h * Sigmoid(net.2 SiLU(net.0 pool(h))) + res with
- * pool(h) = sum_p softmax_p(to_k(h)) h[p].  wk [C], bk [1], w0 [Hd][C], b0 [Hd], w2 [C][Hd], b2 [C].  One thread-block cluster per image keeps h in
- * shared memory; returns SFB_ERR_UNSUPPORTED (no message) when an image's slab does not fit -- callers then use sfb_gca_pool + sfb_linear_small +
- * sfb_gate_mlp_residual_nhwc. */
-int sfb_gca_tail_nhwc(const float* h, int64_t ldh, const float* wk, const float* bk, const float* w0, const float* b0, const float* w2,
-                      const float* b2, int Hd, const float* res, int64_t ldr, float* out, int64_t ldo, int NB, int HW, int C, void* stream);
 /* VAE helpers.  softmax over the columns of every row of scale * x (ldm AttnBlock, model.py:183-190);
  * nearest-neighbour x2 upsampling in NHWC (ldm Upsample, model.py:44-52). */
 int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream);
@@ -335,6 +329,25 @@ int sfb_add_relu_mask(float* g, const float* g_head, const float* act, int64_t n
 /* one tap: f0, f1 [HW][C] feature maps of pred / target, w [C] the non-negative 1x1 `lin` weights.  *value += mean_p sum_c w_c (n0 - n1)^2 with
  * n = f / (||f||_2 + 1e-10) over channels; g_f0 [HW][C] <- d value / d f0 */
 int sfb_lpips_head(const float* f0, const float* f1, const float* w, int HW, int C, float* value, float* g_f0, void* stream);
+
+/* ==========================================================================================
+ * section 8 -- Epipolar Feature Transformer operators (the per-scene EFT feature cache)
+ *    sparsefusion/eft.py:155-470 (encode / index / forward), called from sparsefusion/distillation.py:92-127 through
+ *    utils/eft_renderer.py.  ResNet-18 convolutions (BatchNorm folded) and every nn.Linear of the three transformer encoders use
+ *    sfb_conv2d_nhwc_tf32_ex; these are the NHWC fp32 operators around them.  sparsefusion_b200/eft.py strings them together.
+ * ========================================================================================== */
+/* torchvision resnet maxpool: 3x3 window, stride 2, padding 1; y [NB][(H+1)/2][(W+1)/2][C] */
+int sfb_maxpool3x3s2_nhwc(const float* x, float* y, int NB, int H, int W, int C, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=True) to (Ho, Wo), written with channel stride ldo (eft.py:194-202 pyramid concatenation) */
+int sfb_resize_bilinear_ac_nhwc(const float* x, int64_t ldx, float* y, int64_t ldo, int NB, int H, int W, int C, int Ho, int Wo, void* stream);
+/* F.grid_sample(mode='bilinear', padding_mode='border', align_corners=True) (eft.py:248-275): x [NB][H][W][C] (channel stride ldx),
+ * grid [NB][M][2] = (x, y) in [-1, 1], out [NB][M][C] (row stride ldo) */
+int sfb_grid_sample_nhwc(const float* x, int64_t ldx, const float* grid, float* out, int64_t ldo, int NB, int H, int W, int C, int64_t M, void* stream);
+/* single-head attention core of nn.TransformerEncoderLayer(d_model E, nhead 1), sequence-first: qkv [S][B][3E] = in_proj(x) (q | k | v),
+ * out [S][B][E] = softmax(q k^T / sqrt(E)) v over the S <= 32 positions of each batch element (eft.py:30-33: S = input views or depth samples) */
+int sfb_seq_attention(const float* qkv, float* out, int S, int B, int E, void* stream);
+/* in place over n floats (n % 4 == 0): kind 0 ReLU, 1 GELU (erf) */
+int sfb_act_inplace(float* x, int64_t n, int kind, void* stream);
 
 #ifdef __cplusplus
 }

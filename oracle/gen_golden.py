@@ -155,6 +155,33 @@ def gen_ngp():
     no.write_golden(GOLD)
 
 
+def gen_eft():
+    """tests/golden/eft.npz: outputs of the REFERENCE's own EpipolarFeatureTransformer (sparsefusion/eft.py, imported unmodified; pytorch3d's RayBundle and
+    the two camera methods it calls supplied by oracle/eft_oracle.py) on deterministic weights and inputs: the per-ray colour, the 256-d feature the
+    VLDM is conditioned on, and samples of the ResNet-18 pyramid"""
+    from oracle import eft_oracle as eo
+    from sparsefusion_b200.eft import EpipolarFeatureTransformer as Mirror
+    eft = eo.import_reference_eft(REF)
+    try:
+        ref = eft.EpipolarFeatureTransformer(use_r=True, encoder='resnet18', return_features=True, remove_unused_layers=False).eval()   # utils/load_model.py:34
+    finally:
+        eft._restore_resnet18()
+    mirror = Mirror(use_r=True, encoder='resnet18', return_features=True, remove_unused_layers=False)
+    shapes = {k: tuple(v.shape) for k, v in mirror.state_dict().items()}
+    assert shapes == {k: tuple(v.shape) for k, v in ref.state_dict().items()}, 'the mirror must have the reference state_dict layout'
+    ref.load_state_dict(eo.make_params(shapes, seed=0), strict=True)
+    images, cams, rb = eo.scene_inputs()
+    with torch.no_grad():
+        _, latent = ref.encode(cams, images)
+        rgb, f3, _ = ref.forward(rb)
+        rgb_b, f3_b, _ = ref.batched_forward(eo.RayBundle(rb.origins.view(6, 8, 3), rb.directions.view(6, 8, 3), rb.lengths.view(6, 8, -1), None), n_batches=4)
+    assert torch.allclose(rgb_b.reshape(-1, 3), rgb, atol=1e-6) and torch.allclose(f3_b.reshape(-1, 256), f3, atol=1e-5)    # chunking changes nothing
+    print(f'[eft] latent {tuple(latent.shape)} norm {latent.norm():.3f}; rgb mean {rgb.mean():.4f}; f3 norm {f3.norm():.3f}; {len(shapes)} tensors')
+    flat = latent.permute(0, 2, 3, 1).reshape(-1)
+    np.savez_compressed(os.path.join(GOLD, 'eft.npz'), rgb=rgb.numpy(), f3=f3.numpy(), latent_shape=np.array(latent.shape), latent_norm=float(latent.norm()),
+                        latent_sample=flat[::997].numpy(), n_tensors=len(shapes), param_seed=0, input_seed=3)
+
+
 def _import_reference_ngp():
     """import the REFERENCE's external.nerf.network_grid (NeRFNetwork over renderer_df.NeRFRenderer) on this CPU-only container.  Its module-level
     imports that cannot be satisfied here are replaced by inert stubs (trimesh, mcubes, torch_ema, lpips, ... -- none is touched by run()), and the
@@ -284,7 +311,7 @@ def gen_run_ref():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ['unet', 'plms', 'ngp', 'vae', 'run_ref']
+    which = sys.argv[1:] or ['unet', 'plms', 'ngp', 'vae', 'run_ref', 'eft']
     torch.set_num_threads(os.cpu_count())
     if 'unet' in which:
         gen_unet()
@@ -298,3 +325,5 @@ if __name__ == '__main__':
         gen_vae()
     if 'run_ref' in which:
         gen_run_ref()
+    if 'eft' in which:
+        gen_eft()

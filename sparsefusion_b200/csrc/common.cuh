@@ -45,7 +45,8 @@ int fusion_mask();
 static inline bool wgrad_tc_enabled() { return (fusion_mask() & 1) != 0; }
 static inline bool gn_grid_enabled() { return (fusion_mask() & 2) != 0; }
 static inline bool gn_cluster_enabled() { return (fusion_mask() & 4) != 0; }   // single-launch GroupNorm: one thread-block cluster per (image, group)
-static inline bool gca_cluster_enabled() { return (fusion_mask() & 8) != 0; }  // GlobalContext + gate + residual as one cluster kernel   // single-launch GroupNorm with a software grid barrier (batch 1)
+static inline bool gca_cluster_enabled() { return (fusion_mask() & 8) != 0; }  // GlobalContext + gate + residual as one cluster kernel
+static inline bool gca_cluster_wide() { return (fusion_mask() & 16) != 0; }    // ... with 16-CTA (non-portable) clusters where the slab allows, else 8   // single-launch GroupNorm with a software grid barrier (batch 1)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

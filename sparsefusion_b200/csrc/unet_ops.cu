@@ -12,7 +12,6 @@
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <cooperative_groups.h>
-#include <atomic>
 #include "../../include/sparsefusion_b200.h"
 
 namespace sfb {
@@ -899,273 +898,6 @@ __global__ void __launch_bounds__(256) gate_mlp_residual_kernel(const float* __r
     }
 }
 
-// The whole GlobalContext branch + ResnetBlock tail as ONE launch (imagen_pytorch.py:919-941, :727-729):
-//   logits = to_k(h) -> softmax over pixels -> pooled = sum_p softmax_p h[p] -> hid = SiLU(net.0 pooled) -> gate = Sigmoid(net.2 hid) -> out = h gate + res
-// (four dependent kernels before: logits, pool, GEMV, gate + residual = ~17 us of a ~100 us resnet block at batch 1).  One thread-block CLUSTER of k
-// CTAs per image: every CTA keeps its slab of pixels (all channels) in shared memory for the three uses of h; the softmax statistics, the pooled
-// vector, hid and gate are exchanged through distributed shared memory at three cluster barriers, and the two GEMVs are split over the cluster so
-// that each CTA streams 1/k of their weights.  Deterministic: every fold has a fixed order.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-struct GcaLayout {
-    int xs, lg, pp, pooled, scr, hid_sl, hid, gate_sl, gate, total;   // offsets in floats
-};
-__host__ __device__ inline GcaLayout gca_layout(int Pmax, int C, int Hd, int k) {
-    GcaLayout L;
-    const int hs = (Hd + k - 1) / k, cs = (C + k - 1) / k;
-    auto up4 = [](int v) { return (v + 3) & ~3; };
-    int o = 0;
-    L.xs = o; o += up4(Pmax * C);
-    L.lg = o; o += up4(Pmax);
-    L.pp = o; o += up4(C);
-    L.pooled = o; o += up4(C);
-    L.scr = o; o += up4(C > 1024 ? C : 1024);
-    L.hid_sl = o; o += up4(hs);
-    L.hid = o; o += up4(Hd);
-    L.gate_sl = o; o += up4(cs);
-    L.gate = o; o += up4(C);
-    L.total = o;
-    return L;
-}
-__global__ void __launch_bounds__(256, 1) gca_tail_cluster_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ wk,
-                                                              const float* __restrict__ bk, const float* __restrict__ W0, const float* __restrict__ b0,
-                                                              const float* __restrict__ W2, const float* __restrict__ b2, int Hd,
-                                                              const float* __restrict__ res, int64_t ldr, float* __restrict__ out, int64_t ldo, int HW,
-                                                              int C, int Pmax) {
-    pdl_sync();
-    cg::cluster_group cl = cg::this_cluster();
-    extern __shared__ __align__(16) float gsm[];
-    const int k = (int)cl.num_blocks(), rank = (int)cl.block_rank();
-    const int n = blockIdx.y;
-    const int C4 = C >> 2;
-    const int hs = (Hd + k - 1) / k, cs = (C + k - 1) / k;
-    const GcaLayout L = gca_layout(Pmax, C, Hd, k);
-    float* xs = gsm + L.xs;
-    float* lg = gsm + L.lg;
-    float* pp = gsm + L.pp;
-    float* pooled = gsm + L.pooled;
-    float* scr = gsm + L.scr;
-    float* hid_sl = gsm + L.hid_sl;
-    float* hid = gsm + L.hid;
-    float* gate_sl = gsm + L.gate_sl;
-    float* gate = gsm + L.gate;
-    __shared__ float st_ms[2];          // local softmax max, sum of exponentials
-    __shared__ float wr[17];            // per-rank rescale weights e^{m_r - M}, [16] = 1 / S
-    __shared__ float red[8];
-    const int p0 = (int)(((int64_t)HW * rank) / k), p1 = (int)(((int64_t)HW * (rank + 1)) / k);
-    const int P = p1 - p0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- (1) slab -> shared memory
-    {
-        // 8 independent 16-byte loads in flight per thread: with one load per iteration the 256 threads of the only CTA on this SM would keep 4 KB in
-        // flight and the 64 KB slab would take ~16 L2 round trips (measured: 6 us of the first version's 20)
-        const float* hb = h + ((int64_t)n * HW + p0) * ldh;
-        const int tot = P * C4;
-        for (int i0 = threadIdx.x; i0 < tot; i0 += 256 * 8) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * 256;
-                if (i < tot) {
-                    const int pix = i / C4, c4 = i - pix * C4;
-                    v[u] = __ldg(reinterpret_cast<const float4*>(hb + (int64_t)pix * ldh) + c4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * 256;
-                if (i < tot) reinterpret_cast<float4*>(xs)[i] = v[u];          // xs is [P][C4] dense: index == i
-            }
-        }
-    }
-    __syncthreads();
-    // ---- (2) logits of the slab's pixels, one warp per pixel
-    for (int p = warp; p < P; p += 8) {
-        const float4* xr = reinterpret_cast<const float4*>(xs) + (size_t)p * C4;
-        float d = 0.f;
-        for (int c4 = lane; c4 < C4; c4 += 32) {
-            const float4 v = xr[c4];
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wk) + c4);
-            d += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
-        }
-        d = warp_sum(d);
-        if (lane == 0) lg[p] = d + __ldg(bk);
-    }
-    __syncthreads();
-    // ---- (3) local softmax statistics; lg becomes e^{l - m}
-    float mx = -INFINITY;
-    for (int p = threadIdx.x; p < P; p += 256) mx = fmaxf(mx, lg[p]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-    __syncthreads();
-    float sm = 0.f;
-    for (int p = threadIdx.x; p < P; p += 256) { const float e = __expf(lg[p] - mx); lg[p] = e; sm += e; }
-    sm = warp_sum(sm);
-    if (lane == 0) red[warp] = sm;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w];
-        st_ms[0] = (P > 0) ? mx : -INFINITY;
-        st_ms[1] = t;
-    }
-    // ---- (4) local un-normalised pooled: pp[c] = sum_p e_p x[p][c].  thread = (float4 column, pixel phase); phases fold through scr
-    {
-        const int cols = C4 < 256 ? C4 : 256;
-        const int phases = 256 / cols;                          // >= 1
-        const int col0 = threadIdx.x % cols, ph = threadIdx.x / cols;
-        for (int col = col0; col < C4; col += cols) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ph < phases) {
-                for (int p = ph; p < P; p += phases) {
-                    const float e = lg[p];
-                    const float4 v = reinterpret_cast<const float4*>(xs)[(size_t)p * C4 + col];
-                    acc.x += e * v.x; acc.y += e * v.y; acc.z += e * v.z; acc.w += e * v.w;
-                }
-                if (phases == 1) reinterpret_cast<float4*>(pp)[col] = acc;
-                else reinterpret_cast<float4*>(scr)[ph * C4 + col] = acc;       // phases > 1 implies C4 < 256: one sweep, phases * C <= 1024 floats
-            }
-        }
-        if (phases > 1) {
-            __syncthreads();
-            for (int c = threadIdx.x; c < C; c += 256) {
-                float t = 0.f;
-                for (int q = 0; q < phases; ++q) t += scr[q * C + c];
-                pp[c] = t;
-            }
-        }
-    }
-    cluster_arrive();
-    cluster_wait();                       // (A) every CTA's (m, s) and pp are published
-    // ---- (5) global softmax: M = max m_r, S = sum e^{m_r - M} s_r, pooled = sum_r e^{m_r - M} pp_r / S
-    if (warp == 0) {
-        float m = -INFINITY, sv = 0.f;
-        if (lane < k) {
-            const float* rs = cl.map_shared_rank(st_ms, lane);
-            m = rs[0]; sv = rs[1];
-        }
-        const float M = warp_max(m);
-        const float w = (lane < k && m > -INFINITY) ? __expf(m - M) : 0.f;
-        const float S = warp_sum(w * sv);
-        if (lane < 16) wr[lane] = w;
-        if (lane == 0) wr[16] = 1.f / S;
-    }
-    __syncthreads();
-    {
-        const float inv = wr[16];
-        for (int col = threadIdx.x; col < C4; col += 256) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 v[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r)                                            // all remote loads issued before the first use (DSMEM latency ~215 cycles each)
-                if (r < k) v[r] = reinterpret_cast<const float4*>(cl.map_shared_rank(pp, r))[col];
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-                if (r < k) { const float w = wr[r]; acc.x += w * v[r].x; acc.y += w * v[r].y; acc.z += w * v[r].z; acc.w += w * v[r].w; }
-            reinterpret_cast<float4*>(pooled)[col] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-        }
-    }
-    __syncthreads();
-    // ---- (6) this CTA's rows of hid = SiLU(W0 pooled + b0), one warp per row
-    {
-        const int j0 = rank * hs, j1 = min(Hd, j0 + hs);
-        for (int j = j0 + warp; j < j1; j += 8) {
-            const float4* wrow = reinterpret_cast<const float4*>(W0 + (int64_t)j * C);
-            float acc = 0.f;
-            for (int c0 = lane; c0 < C4; c0 += 32 * 8) {
-                float4 w[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (c0 + u * 32 < C4) w[u] = __ldg(wrow + c0 + u * 32);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (c0 + u * 32 < C4) {
-                        const float4 x = reinterpret_cast<const float4*>(pooled)[c0 + u * 32];
-                        acc += w[u].x * x.x + w[u].y * x.y + w[u].z * x.z + w[u].w * x.w;
-                    }
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) hid_sl[j - j0] = silu_f(acc + __ldg(b0 + j));
-        }
-    }
-    cluster_arrive();
-    cluster_wait();                       // (B) hid slices published
-    for (int j = threadIdx.x; j < Hd; j += 256) {
-        const int r = j / hs;
-        hid[j] = cl.map_shared_rank(hid_sl, r)[j - r * hs];
-    }
-    __syncthreads();
-    // ---- (7) this CTA's channels of gate = Sigmoid(W2 hid + b2), one warp per channel
-    {
-        const int c0 = rank * cs, c1 = min(C, c0 + cs);
-        for (int c = c0 + warp; c < c1; c += 8) {
-            const float* wrow = W2 + (int64_t)c * Hd;
-            float acc = 0.f;
-            if ((Hd & 3) == 0) {
-                const int H4 = Hd >> 2;
-                for (int j0 = lane; j0 < H4; j0 += 32 * 4) {
-                    float4 w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (j0 + u * 32 < H4) w[u] = __ldg(reinterpret_cast<const float4*>(wrow) + j0 + u * 32);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (j0 + u * 32 < H4) {
-                            const float4 x = reinterpret_cast<const float4*>(hid)[j0 + u * 32];
-                            acc += w[u].x * x.x + w[u].y * x.y + w[u].z * x.z + w[u].w * x.w;
-                        }
-                }
-            } else {
-                for (int j = lane; j < Hd; j += 32) acc += __ldg(wrow + j) * hid[j];
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) gate_sl[c - c0] = sigmoid_f(acc + __ldg(b2 + c));
-        }
-    }
-    cluster_arrive();
-    cluster_wait();                       // (C) gate slices published
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const int r = c / cs;
-        gate[c] = cl.map_shared_rank(gate_sl, r)[c - r * cs];
-    }
-    cluster_arrive();                     // (D) this CTA reads no peer's shared memory any more; peers may still read ours until they arrive too
-    __syncthreads();
-    // ---- (8) out = h * gate + res over the slab
-    {
-        const float* rb = res + ((int64_t)n * HW + p0) * ldr;
-        float* ob = out + ((int64_t)n * HW + p0) * ldo;
-        const int tot = P * C4;
-        for (int i0 = threadIdx.x; i0 < tot; i0 += 256 * 8) {
-            float4 r[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * 256;
-                if (i < tot) {
-                    const int pix = i / C4, c4 = i - pix * C4;
-                    r[u] = __ldg(reinterpret_cast<const float4*>(rb + (int64_t)pix * ldr) + c4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * 256;
-                if (i < tot) {
-                    const int pix = i / C4, c4 = i - pix * C4;
-                    const float4 v = reinterpret_cast<const float4*>(xs)[i];
-                    const float4 g = reinterpret_cast<const float4*>(gate)[c4];
-                    *reinterpret_cast<float4*>(ob + (int64_t)pix * ldo + c4 * 4) =
-                        make_float4(v.x * g.x + r[u].x, v.y * g.y + r[u].y, v.z * g.z + r[u].z, v.w * g.w + r[u].w);
-                }
-            }
-        }
-    }
-    cluster_wait();                       // (D) do not exit while a peer may still read this CTA's gate slice
-}
-
 // ------------------------------------------------------------------------------------ VAE helpers (ldm AttnBlock / Upsample)
 // y[r][:] = softmax(scale * x[r][:]) over `cols` columns; one CTA per row (ldm model.py:183-190: single-head attention over h*w tokens)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int cols,
@@ -1409,60 +1141,6 @@ int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, co
     if (NB == 0 || HW == 0) return SFB_OK;
     SFB_LAUNCH(gate_mlp_residual_kernel, dim3(ceil_div(C, 8), NB), 256, 0, as_stream(stream), h, ldh, hid, w2, b2, Hd, res, ldr, out, ldo, HW, C);
     return check_launch("gate_mlp_residual");
-}
-
-static int gca_cluster_size(int HW, int C, int Hd, size_t* smem_out) {
-    // the widest cluster whose CTAs fit their pixel slab in shared memory: 16 (non-portable size, allowed on sm_100) when the device can co-schedule
-    // it, else 8; 0 = no cluster configuration fits (large images: the four-kernel path stays)
-    constexpr size_t kLimit = 200 * 1024;
-    static std::atomic<int> wide_ok[64];                 // per device: 0 unknown, 1 yes, 2 no
-    const int dev = current_device() & 63;
-    for (int k = 16; k >= 8; k >>= 1) {
-        if (HW < k) continue;
-        const int Pmax = (HW + k - 1) / k;
-        const size_t bytes = (size_t)gca_layout(Pmax, C, Hd, k).total * 4;
-        if (bytes > kLimit) continue;
-        if (k == 16) {
-            int okv = wide_ok[dev].load();
-            if (okv == 0) {
-                cudaFuncSetAttribute(gca_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                cudaFuncSetAttribute(gca_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLimit);
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(16, 1, 1);
-                cfg.blockDim = dim3(256, 1, 1);
-                cfg.dynamicSmemBytes = kLimit;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
-                int nclusters = 0;
-                const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, gca_tail_cluster_kernel, &cfg);
-                okv = (e == cudaSuccess && nclusters > 0) ? 1 : 2;
-                if (e != cudaSuccess) cudaGetLastError();
-                wide_ok[dev].store(okv);
-            }
-            if (okv != 1) continue;
-        }
-        *smem_out = bytes;
-        return k;
-    }
-    return 0;
-}
-
-int sfb_gca_tail_nhwc(const float* h, int64_t ldh, const float* wk, const float* bk, const float* w0, const float* b0, const float* w2,
-                      const float* b2, int Hd, const float* res, int64_t ldr, float* out, int64_t ldo, int NB, int HW, int C, void* stream) {
-    SFB_REQUIRE(h && wk && bk && w0 && b0 && w2 && b2 && res && out, "gca_tail: null pointer");
-    SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && Hd > 0, "gca_tail: channel counts must be multiples of 4");
-    if (NB == 0 || HW == 0) return SFB_OK;
-    size_t smem = 0;
-    const int k = gca_cluster_enabled() ? gca_cluster_size(HW, C, Hd, &smem) : 0;
-    if (k == 0) return SFB_ERR_UNSUPPORTED;      // caller falls back to gca_pool + linear_small + gate_mlp_residual
-    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(gca_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
-    SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(gca_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
-    const int Pmax = (HW + k - 1) / k;
-    SFB_LAUNCH_CLUSTER(gca_tail_cluster_kernel, dim3(k, NB), 256, smem, as_stream(stream), (unsigned)k, h, ldh, wk, bk, w0, b0, w2, b2, Hd, res, ldr, out, ldo,
-                       HW, C, Pmax);
-    return check_launch("gca_tail");
 }
 
 int sfb_softmax_rows(const float* x, int64_t ldx, float* y, int64_t ldy, int rows, int cols, float scale, void* stream) {

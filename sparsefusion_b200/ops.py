@@ -359,25 +359,6 @@ def gca_pool(x: torch.Tensor, wk: torch.Tensor, bk: torch.Tensor) -> torch.Tenso
     return pooled
 
 
-def gca_tail(h: torch.Tensor, wk: torch.Tensor, bk: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
-             res: torch.Tensor) -> Optional[torch.Tensor]:
-    """GlobalContext branch + ResnetBlock tail in one cluster kernel: h * sigmoid(w2 silu(w0 pool(h) + b0) + b2) + res; None when an image's pixel
-    slab does not fit the cluster's shared memory (the caller then runs gca_pool + linear_small + gate_mlp_residual)"""
-    nb, hh, ww, c, ldh = _nhwc_meta(h)
-    _, _, _, _, ldr = _nhwc_meta(res)
-    hd = w0.shape[0]
-    assert tuple(w0.shape) == (hd, c) and tuple(w2.shape) == (c, hd) and w0.is_contiguous() and w2.is_contiguous()
-    out = torch.empty(nb, hh, ww, c, dtype=torch.float32, device=h.device)
-    wk = wk.reshape(-1)
-    rc = lib.load().sfb_gca_tail_nhwc(h.data_ptr(), ldh, lib.fptr(wk), lib.fptr(bk), lib.fptr(w0), lib.fptr(b0), lib.fptr(w2), lib.fptr(b2), hd, res.data_ptr(), ldr,
-                                      out.data_ptr(), c, nb, hh * ww, c, lib.stream())
-    if rc == 3:          # SFB_ERR_UNSUPPORTED
-        return None
-    if rc != 0:
-        raise RuntimeError(f'sfb_gca_tail_nhwc: {lib.load().sfb_last_error().decode()}')
-    return out
-
-
 def gate_residual(h: torch.Tensor, gate: Optional[torch.Tensor], res: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, hh, ww, c, ldh = _nhwc_meta(h)
     ldr = _nhwc_meta(res)[4]

@@ -1,33 +1,50 @@
-"""diagnostic: per-view finiteness / agreement of the batched VAE + PLMS path (small configuration)"""
+"""diagnostic: per-view agreement of every stage of the view-batched fusion term across batch compositions (small configuration)"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from test_minibatch_gpu import _build, _fixed_target
+from sparsefusion_b200 import image_glue as glue
 
 dev = torch.device('cuda', 0)
 res = {}
 for V in (1, 2, 4):
     d = _build(0, 1, dev, V)
-    seen = {}
-    def hook(views, pred_img, seen=seen):
-        for j, v in enumerate(views):
-            seen[v] = pred_img[j].clone()
-        return _fixed_target(views, pred_img)
-    d.pred_img_hook = hook
+    rec = {}
+    cur = {}
+    orig_up = glue.upsample2x_render
+    ups = []
+    def up_hook(img, ws, h, w, ups=ups):
+        out = orig_up(img, ws, h, w)
+        ups.append(out.clone())
+        return out
+    glue.upsample2x_render = up_hook
+    orig_encode = d.vae.encode
+    def enc(x, cur=cur):
+        p = orig_encode(x)
+        cur['lat'] = p.mode().clone()
+        return p
+    d.vae.encode = enc
     orig_sample = d.sampler.sample
-    def sample(latents, **kw):
+    def sample(latents, cur=cur, **kw):
         out = orig_sample(latents, **kw)
-        print(f'  V={V}: latents finite {torch.isfinite(latents).all().item()} absmax {latents.abs().max().item():.3f}; pred_x0 finite per row '
-              f'{[torch.isfinite(out[0][i]).all().item() for i in range(out[0].shape[0])]} absmax {out[0].abs().max().item():.3f}')
+        cur['x0'] = out[0].clone()
         return out
     d.sampler.sample = sample
+    def hook(views, pred_img, rec=rec, cur=cur, ups=ups):
+        for j, v in enumerate(views):
+            rec[v] = dict(up=ups[j], lat=cur['lat'][j], x0=cur['x0'][j], img=pred_img[j].clone())
+        return _fixed_target(views, pred_img)
+    d.pred_img_hook = hook
     d.minibatch_step(1500, max_thres=0.05)
     torch.cuda.synchronize()
-    for v, img in seen.items():
-        print(f'  V={V} view {v}: pred_img finite {torch.isfinite(img).all().item()} min {img.min().item():.4f} max {img.max().item():.4f} mean {img.mean().item():.4f}')
-    res[V] = seen
+    glue.upsample2x_render = orig_up
+    print(f'V={V}: views {d.last["views"]}')
+    res[V] = rec
+rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30)).item()
 for v in res[4]:
     for V in (1, 2):
         if v in res[V]:
-            print(f'view {v}: batch {V} vs batch 4 max abs diff {(res[V][v] - res[4][v]).abs().max().item():.3e}')
+            a, b = res[V][v], res[4][v]
+            print(f'view {v}: batch {V} vs batch 4: render-up rel {rel(a["up"], b["up"]):.2e}  latents {rel(a["lat"], b["lat"]):.2e}  pred_x0 {rel(a["x0"], b["x0"]):.2e}  '
+                  f'pred_img rel {rel(a["img"], b["img"]):.2e} maxabs {(a["img"] - b["img"]).abs().max().item():.2e}')

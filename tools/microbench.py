@@ -82,6 +82,9 @@ def unet_trace(out):
         _lib.call('sfb_set_pdl', 3)
     if 'padsmem' in sys.argv:
         _lib.call('sfb_set_pdl', 5)
+    for a in sys.argv:
+        if a.startswith('fuse='):
+            _lib.call('sfb_set_fusion', int(a[5:], 0))
     from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
     unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
