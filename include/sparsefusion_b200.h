@@ -165,6 +165,12 @@ int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int6
 int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH,
                             int KW, int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                             int accumulate, int splits, int bn, void* stream);
+/* same kernel as a general GEMM whose K-major "weight" operand w [Cout][KH*KW*ceil32(Cin)] is NOT a parameter but the output of an earlier launch on the
+ * same stream (q k^T and P v of the VAE's attention, ldm model.py:183-199): the kernel then does not prefetch it ahead of the programmatic-dependent-
+ * launch wait.  With sfb_conv2d_nhwc_tf32_ex such an operand may be read before the kernel that produces it has run. */
+int sfb_conv2d_nhwc_tf32_dyn(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w, int Cout, int KH, int KW, int stride, int pad,
+                             int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate, int splits,
+                             int bn, void* stream);
 int sfb_conv_weight_k(int Cin, int KH, int KW);
 /* per-launch CUDA-event timing of the conv kernel for the roofline line of bench.py (off by default; do not enable under graph capture) */
 int sfb_conv_prof_enable(int on);
@@ -184,10 +190,9 @@ int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
 /* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
  * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch (fp64 partial statistics per pixel slab).
- * counters: at least 2 uint32 that are ZERO before the first call and are then only touched by this function: the batch-1 path is ONE
- * launch whose <= 128 co-resident CTAs meet at a software grid barrier (counters[0] = arrivals, reset by the last arriver; counters[1] =
- * generation), so the words are reusable call after call; do not share them between calls that may run concurrently on different
- * streams.  NULL selects the two-launch path (statistics kernel + apply kernel), which is also what batches > 1 and large images use.
+ * Groups of >= 16 channels whose per-CTA slab fits the register file: ONE launch, one thread-block cluster of <= 8 CTAs per (image, group), partial
+ * sums exchanged through distributed shared memory (any batch size).  Otherwise two launches (row-coalesced statistics kernel + apply kernel).
+ * counters: unused since ABI 3 (round 1's single-launch variant met at a software grid barrier through these words); pass NULL.
  * Output is TF32-rounded in single-pass mode (it feeds the conv). */
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
                        int64_t film_ld, int act_silu, float eps, float* stats_ws, unsigned int* counters, float* y, int64_t ldy,

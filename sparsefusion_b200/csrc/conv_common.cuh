@@ -28,6 +28,7 @@ struct alignas(64) ConvGemmParams {
     int32_t k_iters, splits;
     int32_t accumulate;
     int32_t presplit;       // tmB / tmBlo hold (hi, lo) of the weights: the converter leaves the N-side tile alone
+    int32_t w_dynamic;      // the "weight" operand was produced by an earlier kernel of this stream (attention GEMMs): no prefetch before griddepcontrol.wait
     int32_t raw_hi;         // experiment (variant 3): feed the un-masked fp32 word as the "hi" tensor-core operand (is the hardware's tf32 read a truncation?)
 };
 

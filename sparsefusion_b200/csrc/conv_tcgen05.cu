@@ -381,6 +381,17 @@ int sfb_conv2d_nhwc_tf32_pad(const float* x, int NB, int H, int W, int Cin, int6
                                    splits, bn, stream);
 }
 
+static thread_local int t_w_dynamic = 0;
+int sfb_conv2d_nhwc_tf32_dyn(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w, int Cout, int KH, int KW, int stride, int pad,
+                             int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo, int accumulate, int splits,
+                             int bn, void* stream) {
+    t_w_dynamic = 1;
+    const int rc = sfb_conv2d_nhwc_tf32_ex(x, NB, H, W, Cin, ldx, w, nullptr, Cout, KH, KW, stride, pad, pad_after, bias, residual, ldr, out, ldo, accumulate,
+                                           splits, bn, stream);
+    t_w_dynamic = 0;
+    return rc;
+}
+
 int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64_t ldx, const float* w_packed, const float* w_hi_lo, int Cout, int KH, int KW,
                             int stride, int pad, int pad_after, const float* bias, const float* residual, int64_t ldr, float* out, int64_t ldo,
                             int accumulate, int splits, int bn, void* stream) {
@@ -422,6 +433,7 @@ int sfb_conv2d_nhwc_tf32_ex(const float* x, int NB, int H, int W, int Cin, int64
     p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
     p.out = out; p.bias = bias; p.ldo = ldo; p.accumulate = accumulate;
     p.raw_hi = (g_variant == 3) ? 1 : 0;
+    p.w_dynamic = t_w_dynamic;
     p.residual = residual; p.ldr = ldr;
     SFB_REQUIRE(residual == nullptr || (ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0), "conv2d_nhwc_tf32: residual must be 16-byte aligned");
 

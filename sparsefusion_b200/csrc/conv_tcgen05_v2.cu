@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_v2_kernel(const __grid_
             const int pre = niter < S ? niter : S;
             phase_mark(pslot, 1);
             pdl_trigger();
+            // ... unless the "weights" are themselves the output of an earlier kernel (q k^T, P v of the VAE's attention): prologues of a PDL chain run
+            // arbitrarily far ahead of the bodies, so such an operand may not exist yet -- wait first (found as intermittent NaN in the decoded image)
+            if (p.w_dynamic) pdl_wait();
             for (int it = 0; it < pre; ++it) {
                 tc::mbar_expect_tx(&wfull_bar[it], w_tx);
                 load_weights(it);

@@ -201,140 +201,13 @@ __global__ void __launch_bounds__(256) gn_stats_rows_kernel(const float* __restr
     }
 }
 
-// Single-launch GroupNorm for one image (the batch-1 UNet evaluation): statistics, a software grid barrier, normalise -- x is read ONCE and
-// stays in registers across the barrier.  grid = S <= 128 CTAs of 256 threads (all co-resident: one per SM at most, a few KB of smem), CTA s owns
-// a slab of whole pixel rows; thread t keeps float4 column (t % cols) of <= 8 rows (two passes when C/4 > 256).
-//   phase 1: per-thread fp64 (sum, sumsq) of its column -> shared memory -> one thread per group folds the CTA's columns -> partial[g][s]
-//   barrier: arrive on a counter; the last arriver bumps a generation word, the others poll it (sense-reversing, reusable across launches)
-//   phase 2: every CTA folds the S partials of each group (one warp per group), then y = silu(((x - mean) rstd gamma + beta)(scale + 1) + shift)
-// Saves one dependent launch (~2 us) and the re-read of x against gn_stats_rows_kernel + gn_apply_kernel: 9.6 -> ~6 us per GroupNorm in the
-// replayed graph, 54 GroupNorms per evaluation.
 constexpr int kGnMaxGroups = 32;
 constexpr int kGnMaxSlabs = 256;   // partials per (image, group): sizes the workspace (sfb_groupnorm_ws_floats)
-constexpr int kGnGridItems = 8;     // float4 per thread held across the barrier
-constexpr int kGnGridMaxCtas = 128;
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__global__ void __launch_bounds__(256) gn_grid_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ film,
-                                                      double2* __restrict__ partial, unsigned int* __restrict__ bar, float* __restrict__ y, int64_t ldy,
-                                                      int act, int round) {
-    pdl_sync();
-    __shared__ double sh_s[256], sh_ss[256];
-    __shared__ float2 st_sh[kGnMaxGroups];
-    __shared__ unsigned int sh_gen;
-    const int S = gridDim.x, sl = blockIdx.x;
-    const int C4 = C >> 2, Cg = C / G, Cg4 = Cg >> 2;
-    const int cols = C4 < 256 ? C4 : 256, passes = C4 < 256 ? 1 : C4 / 256;
-    const int rpi = 256 / cols;
-    const int p0 = (int)(((int64_t)HW * sl) / S), p1 = (int)(((int64_t)HW * (sl + 1)) / S);
-    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-    const int gpp = cols / Cg4;
-    const int rows_it = max(1, (p1 - p0 + rpi - 1) / rpi);  // block iterations per pass (host guarantees passes * rows_it <= kGnGridItems)
-    float4 v[kGnGridItems];
-    if (threadIdx.x == 0) sh_gen = ld_acquire_u32(bar + 1);   // generation BEFORE arriving (it only changes once every CTA has arrived)
-    // ---- phase 1
-#pragma unroll
-    for (int k = 0; k < kGnGridItems; ++k) {
-        const int pass = k / rows_it, it = k - pass * rows_it;   // rows_it >= 1
-        const int p = p0 + tr + it * rpi;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pass < passes && p < p1) v[k] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)p * ldx + (pass * 256 + tc) * 4));
-    }
-    for (int pass = 0; pass < passes; ++pass) {
-        double s = 0.0, ss = 0.0;
-#pragma unroll
-        for (int k = 0; k < kGnGridItems; ++k) {
-            if (k / rows_it == pass) {
-                s += (double)(v[k].x + v[k].y + v[k].z + v[k].w);
-                ss += (double)(v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w);
-            }
-        }
-        sh_s[threadIdx.x] = s;
-        sh_ss[threadIdx.x] = ss;
-        __syncthreads();
-        if (threadIdx.x < gpp) {
-            double ts = 0.0, tss = 0.0;
-            for (int r = 0; r < rpi; ++r)
-                for (int j = 0; j < Cg4; ++j) {
-                    const int i = r * cols + threadIdx.x * Cg4 + j;
-                    ts += sh_s[i];
-                    tss += sh_ss[i];
-                }
-            partial[(int64_t)(pass * gpp + threadIdx.x) * S + sl] = make_double2(ts, tss);
-        }
-        __syncthreads();
-    }
-    // ---- grid barrier
-    if (threadIdx.x == 0) {
-        const unsigned int gen = sh_gen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == (unsigned int)(S - 1)) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicExch(bar + 1, gen + 1u);
-        } else {
-            while (ld_acquire_u32(bar + 1) == gen) {}
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    // ---- phase 2
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int g = warp; g < G; g += 8) {
-        double ts = 0.0, tss = 0.0;
-        for (int k = lane; k < S; k += 32) {
-            const double2 pr = __ldcg(partial + (int64_t)g * S + k);
-            ts += pr.x; tss += pr.y;
-        }
-        ts = warp_sum_d(ts);
-        tss = warp_sum_d(tss);
-        if (lane == 0) {
-            const double cnt = (double)HW * Cg;
-            const double mean = ts / cnt;
-            double var = tss / cnt - mean * mean;
-            if (var < 0) var = 0;
-            st_sh[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kGnGridItems; ++k) {
-        const int pass = k / rows_it, it = k - pass * rows_it;
-        const int p = p0 + tr + it * rpi;
-        if (pass < passes && p < p1) {
-            const int c = (pass * 256 + tc) * 4;
-            const float2 st = st_sh[c / Cg];
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-            float o[4] = {(v[k].x - st.x) * st.y * ga.x + be.x, (v[k].y - st.x) * st.y * ga.y + be.y, (v[k].z - st.x) * st.y * ga.z + be.z,
-                          (v[k].w - st.x) * st.y * ga.w + be.w};
-            if (film) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + c));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + C + c));
-                o[0] = o[0] * (sc.x + 1.f) + sh.x; o[1] = o[1] * (sc.y + 1.f) + sh.y;
-                o[2] = o[2] * (sc.z + 1.f) + sh.z; o[3] = o[3] * (sc.w + 1.f) + sh.w;
-            }
-            if (act) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
-            }
-            if (round) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = tc::round_tf32(o[e]);
-            }
-            *reinterpret_cast<float4*>(y + (int64_t)p * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-    }
-}
-
-// Single launch WITHOUT a grid barrier: groups are independent, so each (image, group) gets its own thread-block CLUSTER of k CTAs that split the
-// pixels; a CTA keeps its slab of the group's channels in registers (<= ITEMS float4 per thread), the k partial (sum, sumsq) pairs meet through
-// distributed shared memory at one cluster barrier (a few hundred ns, against ~2 us for the software grid barrier above plus its 128-way partial
-// fold), and every CTA normalises its own slab.  Works for any batch size (grid (G k, NB)); deterministic (fixed fold order, fp64 partials).
+// Single launch: groups are independent, so each (image, group) gets its own thread-block CLUSTER of k CTAs that split the pixels; a CTA keeps
+// its slab of the group's channels in registers (<= ITEMS float4 per thread), the k partial (sum, sumsq) pairs meet through distributed shared
+// memory at one cluster barrier (a few hundred ns), and every CTA normalises its own slab: 6.0 us per GroupNorm in the replayed batch-1 graph.
+// (Round 1 used one launch with a SOFTWARE grid barrier over <= 128 co-resident CTAs -- 8.9 us, and a spin-wait that could hang under MPS /
+// green contexts; it is gone.)  Works for any batch size (grid (G k, NB)); deterministic (fixed fold order, fp64 partials).
 template <int ITEMS>
 __global__ void __launch_bounds__(256) gn_cluster_kernel(const float* __restrict__ x, int64_t ldx, int HW, int C, int G, float eps,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ film,
@@ -1016,22 +889,6 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
             else e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<32>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
             (void)e;
             return check_launch("groupnorm_nhwc(cluster)");
-        }
-    }
-    if (NB == 1 && counters != nullptr && gn_grid_enabled() && (Cg % 4 == 0) && (C4 <= 256 ? (256 % C4 == 0) : (C4 % 256 == 0)) &&
-        (Cg / 4 <= (C4 < 256 ? C4 : 256))) {
-        // single launch with a grid barrier: S CTAs, each holding <= kGnGridItems float4 per thread
-        const int cols = C4 < 256 ? C4 : 256, passes = C4 < 256 ? 1 : C4 / 256, rpi = 256 / cols;
-        const int max_rows = (kGnGridItems / passes) * rpi;                     // pixel rows one CTA can hold
-        int S = max_rows > 0 ? (HW + max_rows - 1) / max_rows : 1 << 30;
-        if (passes <= kGnGridItems && S <= kGnGridMaxCtas && S <= sm_count()) {
-            // spread over more CTAs when there is room (shorter per-CTA chains), keeping every slab non-empty
-            // (measured per launch in the replayed graph: 11.6 us with the minimum CTA count, 9.8 at <= 32, 8.9 at <= 128)
-            while (S * 2 <= kGnGridMaxCtas && S * 2 <= sm_count() && HW / (S * 2) >= rpi) S *= 2;
-            if (S > HW) S = HW;
-            SFB_LAUNCH(gn_grid_kernel, dim3(S), 256, 0, st, x, ldx, HW, C, G, eps, gamma, beta, film, partial, counters, y, ldy, act_silu,
-                       (int)(precision_mode() == 0));
-            return check_launch("groupnorm_nhwc(grid)");
         }
     }
     const bool rows_ok = (Cg % 4 == 0) && (C4 <= 256 ? (256 % C4 == 0) : (C4 % 256 == 0)) && (Cg / 4 <= (C4 < 256 ? C4 : 256));

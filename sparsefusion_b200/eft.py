@@ -195,7 +195,8 @@ class EpipolarFeatureTransformer(nn.Module):
         return y
 
     def _transformer(self, t: str, x: torch.Tensor, S: int, Bn: int) -> torch.Tensor:
-        """TransformerEncoder.forward (eft.py:37-50) on tokens x [S*Bn, d_in(+pad)] in sequence-major order -> [S*Bn, 256]"""
+        """TransformerEncoder.forward (eft.py:37-50) on tokens x [S*Bn, d_in rounded up to a multiple of 4, pad columns zero] in sequence-major order
+        -> [S*Bn, 256] (the packed weights are zero-padded to the next multiple of 32 columns, so the pad columns contribute nothing)"""
         h = self._linear(f'{t}.pre', x, act=1)                                                       # Linear + GELU
         B = self._plan['B']
         for l in range(4):                                                                           # post-norm encoder layers, ReLU feed-forward
@@ -293,7 +294,7 @@ class EpipolarFeatureTransformer(nn.Module):
             tok1[..., :78] = ref_plucker.reshape(NC, M, 78)
             tok1[..., 78:91] = depths.reshape(1, M, 13)
             # ---- T1: sequence = input views, batch = ray samples
-            f1 = self._transformer('t1', tok1.view(NC * M, d1p)[:, :d1], NC, M)                      # [NC*M,256]
+            f1 = self._transformer('t1', tok1.view(NC * M, d1p), NC, M)                                  # zero pad columns meet zero pad weights                      # [NC*M,256]
             # ---- T2: sequence = depth samples, batch = (view, ray)
             d2 = (2 if self.use_r else 1) * 78 + 13 + 256
             d2p = (d2 + 3) // 4 * 4
@@ -306,7 +307,7 @@ class EpipolarFeatureTransformer(nn.Module):
                 o += 78
             t2v[..., o:o + 13] = depths.permute(1, 0, 2)[:, None]
             t2v[..., o + 13:o + 13 + 256] = f1.view(NC, N, D, 256).permute(2, 0, 1, 3)
-            f2 = self._transformer('t2', tok2.view(D * NC * N, d2p)[:, :d2], D, NC * N).view(D, NC, N, 256)
+            f2 = self._transformer('t2', tok2.view(D * NC * N, d2p), D, NC * N).view(D, NC, N, 256)
             sd = self._plan['sd']
             t2 = torch.einsum('dcnf,f->dcn', f2, sd['t2_attn.weight'][0]) + sd['t2_attn.bias']      # Linear(256, 1)
             t2_w = torch.softmax(t2, dim=0)                                                          # over the depth samples (eft.py:415)
@@ -321,7 +322,7 @@ class EpipolarFeatureTransformer(nn.Module):
                 tok3[..., o:o + 78] = ref_plucker[:, :, D // 2, :]
                 o += 78
             tok3[..., o:o + 256] = f2
-            f3 = self._transformer('t3', tok3.view(NC * N, d3p)[:, :d3], NC, N).view(NC, N, 256)
+            f3 = self._transformer('t3', tok3.view(NC * N, d3p), NC, N).view(NC, N, 256)
             t3_w = torch.softmax(torch.einsum('cnf,f->cn', f3, sd['t3_attn.weight'][0]) + sd['t3_attn.bias'], dim=0)   # over the views (eft.py:436)
             f3 = (f3 * t3_w[..., None]).sum(dim=0)                                                   # [N,256]
             rgb = f3 @ sd['color_layer.0.weight'].t() + sd['color_layer.0.bias']

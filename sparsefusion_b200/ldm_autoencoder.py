@@ -196,10 +196,12 @@ class _Sm100Engine:
             rows = hn[b].reshape(n, c)
             q = ops.linear_tc(rows, self.W[pfx + '.q'], c, bias=self.B[pfx + '.q'], w_split=self.S[pfx + '.q'])
             k = ops.linear_tc(rows, self.W[pfx + '.k'], c, bias=self.B[pfx + '.k'], w_split=self.S[pfx + '.k'])
-            scores = ops.linear_tc(q, k, n)                           # q k^T: the keys are the GEMM's [Cout = n][K = c] operand
+            # in these three GEMMs the K-major "weight" operand is an ACTIVATION made by an earlier launch: dynamic_weights keeps the kernel from
+            # prefetching it ahead of its programmatic-dependent-launch wait (the prologues of a PDL chain run far ahead of the bodies)
+            scores = ops.linear_tc(q, k, n, dynamic_weights=True)     # q k^T: the keys are the GEMM's [Cout = n][K = c] operand
             probs = ops.softmax_rows(scores, scale=float(c) ** -0.5)
-            vt = ops.linear_tc(wv, rows, n)                           # (W_v h^T) = v^T without bias: [c][n], the K-major operand of P.V
-            o = ops.linear_tc(probs, vt, c, bias=self.B[pfx + '.v'])   # rows of P sum to 1, so v's bias is added once per output row
+            vt = ops.linear_tc(wv, rows, n, dynamic_weights=True)     # (W_v h^T) = v^T without bias: [c][n], the K-major operand of P.V
+            o = ops.linear_tc(probs, vt, c, bias=self.B[pfx + '.v'], dynamic_weights=True)   # rows of P sum to 1, so v's bias is added once per output row
             ops.linear_tc(o, self.W[pfx + '.proj_out'], c, bias=self.B[pfx + '.proj_out'], residual=x[b].reshape(n, c), out=out[b].reshape(n, c),
                           w_split=self.S[pfx + '.proj_out'])
         return out

@@ -154,7 +154,7 @@ def _conv_out(shape, device):
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 accumulate: bool = False, splits: int = 0, bn: int = 0, pad_after: Optional[int] = None,
-                w_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+                w_split: Optional[torch.Tensor] = None, dynamic_weights: bool = False) -> torch.Tensor:
     nb, h, w, cin, ldx = _nhwc_meta(x)
     if pad_after is None:
         pad_after = pad
@@ -172,14 +172,22 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, cout: int, kh: int, kw:
         assert (rnb, rh, rw, rc) == (nb, ho, wo, cout)
     if w_split is not None:
         assert w_split.shape == (2,) + tuple(w_packed.shape)
+    if dynamic_weights:
+        # the K-major operand is an activation produced by an earlier launch (attention GEMMs): the kernel must not prefetch it ahead of its
+        # programmatic-dependent-launch wait (sfb_conv2d_nhwc_tf32_dyn)
+        assert w_split is None
+        lib.call('sfb_conv2d_nhwc_tf32_dyn', x.data_ptr(), nb, h, w, cin, ldx, lib.fptr(w_packed, 'w_packed'), cout, kh, kw, stride, pad, pad_after,
+                 lib.fptr(bias, 'bias'), None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
+        return out
     lib.call('sfb_conv2d_nhwc_tf32_ex', x.data_ptr(), nb, h, w, cin, ldx,
              lib.fptr(w_packed, 'w_packed'), lib.fptr(w_split, 'w_split'), cout, kh, kw, stride, pad, pad_after, lib.fptr(bias, 'bias'),
              None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, int(accumulate), splits, bn, lib.stream())
     return out
 
 
-def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=None, residual=None, out=None, w_split=None) -> torch.Tensor:
-    """nn.Linear on the tensor cores: rows [T, K] are treated as T 1x1 'images'"""
+def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=None, residual=None, out=None, w_split=None,
+              dynamic_weights: bool = False) -> torch.Tensor:
+    """nn.Linear on the tensor cores: rows [T, K] are treated as T 1x1 'images'.  ``dynamic_weights``: w_packed is an activation (see conv2d_nhwc)"""
     t, k, ld = _rows_meta(x)
     x4 = x.as_strided((t, 1, 1, k), (ld, ld, ld, 1))
     zeroed = False
@@ -191,7 +199,7 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, out_features: int, bias=N
     if residual is not None:
         tr, cr, ldr = _rows_meta(residual)
         r4 = residual.as_strided((t, 1, 1, out_features), (ldr, ldr, ldr, 1))
-    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed, w_split=w_split)
+    conv2d_nhwc(x4, w_packed, out_features, 1, 1, 1, 0, bias, r4, o4, accumulate=zeroed, w_split=w_split, dynamic_weights=dynamic_weights)
     return out
 
 
@@ -262,25 +270,6 @@ def pixel_shuffle_silu(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
 
 
 # --------------------------------------------------------------------------------------------- norms
-_GN_COUNTERS = {}
-
-
-def _gn_counters(device, n: int) -> torch.Tensor:
-    """barrier words of the single-launch GroupNorm (zero before first use; the kernel leaves them reusable).  Inside a UNet evaluation every
-    call takes its OWN words from the evaluation's zero arena, so nothing is shared between launches; elsewhere (VAE, stand-alone calls) one
-    persistent set per device serves the calls of the current stream one after the other."""
-    if _arena is not None:
-        t = _arena.take((64,))
-        if t is not None:
-            return t
-    key = (device.type, device.index)
-    t = _GN_COUNTERS.get(key)
-    if t is None or t.numel() < n:
-        t = torch.zeros(max(n, 64), dtype=torch.int32, device=device)
-        _GN_COUNTERS[key] = t
-    return t
-
-
 def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor, film: Optional[torch.Tensor] = None,
               silu: bool = True, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, h, w, c, ldx = _nhwc_meta(x)
@@ -288,14 +277,13 @@ def groupnorm(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Ten
         out = torch.empty(nb, h, w, c, dtype=torch.float32, device=x.device)
     ldy = _nhwc_meta(out)[4]
     ws = torch.empty(lib.load().sfb_groupnorm_ws_floats(nb, groups), dtype=torch.float32, device=x.device)
-    counters = _gn_counters(x.device, 2)
     film_ld = 0
     if film is not None:
         assert film.shape == (nb, 2 * c) and film.stride(1) == 1
         film_ld = film.stride(0)
     lib.call('sfb_groupnorm_nhwc', x.data_ptr(), ldx, nb, h * w, c, groups, lib.fptr(gamma), lib.fptr(beta), None if film is None else film.data_ptr(),
              film_ld, int(silu), float(eps),
-             lib.fptr(ws), counters.data_ptr(), out.data_ptr(), ldy, lib.stream())
+             lib.fptr(ws), None, out.data_ptr(), ldy, lib.stream())
     return out
 
 

@@ -36,10 +36,10 @@ def test_pixel_shuffle_silu():
     _close(ops.pixel_shuffle_silu(y), ref, 1e-5)
 
 
-@pytest.fixture(params=[0x7fffffff, 0x7fffffff & ~4, 0x7fffffff & ~4 & ~2], ids=['gn-cluster', 'gn-grid-barrier', 'gn-two-launch'])
+@pytest.fixture(params=[0x7fffffff, 0x7fffffff & ~4], ids=['gn-cluster', 'gn-two-launch'])
 def gn_path(request):
-    """GroupNorm paths: one thread-block cluster per (image, group) (sfb_set_fusion bit 2; groups of >= 16 channels) / batch-1 single launch with a
-    software grid barrier (bit 1) / statistics kernel + apply kernel"""
+    """GroupNorm paths: one launch, one thread-block cluster per (image, group) (sfb_set_fusion bit 2; groups of >= 16 channels) / statistics kernel +
+    apply kernel (everything else, and every shape when the bit is cleared)"""
     from sparsefusion_b200 import _lib as lib
     lib.call('sfb_set_fusion', request.param)
     yield request.param
@@ -57,7 +57,7 @@ def test_groupnorm_film_silu(shape, film, gn_path):
     gamma, beta = torch.randn(c, device='cuda'), torch.randn(c, device='cuda')
     fm = torch.randn(nb, 2 * c, device='cuda') if film else None
     y = ops.groupnorm(x, g, gamma, beta, fm, silu=True)
-    y_again = ops.groupnorm(x, g, gamma, beta, fm, silu=True)          # the barrier words must be reusable launch after launch
+    y_again = ops.groupnorm(x, g, gamma, beta, fm, silu=True)          # deterministic: fixed fold orders, no atomics
     assert torch.equal(y, y_again)
     ref = F.group_norm(x.permute(0, 3, 1, 2).double(), g, gamma.double(), beta.double(), eps=1e-5)
     if film:
