@@ -345,6 +345,9 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(float(np.mean(n_calls)) if n_calls else 38.0)
 
+    c5 = None
+    if args.c5 or (world == 8 and not args.no_c5):
+        c5 = c5_leg(device, rank, world, barrier)
     c2 = gref = None
     if rank == 0 and world == 1 and not args.no_c2:
         try:
@@ -375,7 +378,7 @@ def run_gpu(args):
                'step_semantics': ('reference iteration: photometric update, then fusion update on ONE target view (distillation.py:244-247,:345-352)' if V is None else
                                   f'view-batched step (SURVEY 8e): grad(photometric) + mean over {V} target views, {V // world if V >= world else 1} per rank as one UNet/VAE batch, '
                                   'ONE all-reduce and ONE Adam update per step'),
-               'c4_fixed_views': c4, 'c2_render': c2, 'gpu_reference': gref}
+               'c4_fixed_views': c4, 'c2_render': c2, 'c5_large_latents': c5, 'gpu_reference': gref}
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -469,6 +472,70 @@ def c2_leg(ngp, device, n_views=64, hw=256):
     out['workload'] = f'{n_views} views x {hw}x{hw} rays x (64+64) samples, forward only (no_grad), fused run() renderer'
     out['note'] = ('fully fused render is FP32-SIMT / L2-gather bound, not HBM bound (SURVEY 8d): the meaningful fractions are fp32_tflops against the '
                    '~80 TFLOP/s FP32 SIMT peak; each point is evaluated once (the reference evaluates the field twice per point)')
+    return out
+
+
+def c5_leg(device, rank, world, barrier, steps=2, warmup=1):
+    """BASELINE configs[4]: the iteration at 128x128x4 latents -- 1024x1024 images through the VAE and LPIPS, 512x512 rays x (64+64) samples,
+    UNet 1004 GFLOP per evaluation with 256 x 259 attention at the lowest stage, 6 input views -- one target view per GPU per step (reference semantics on
+    every rank, replicas: no collective inside the leg, so a failing rank cannot stall the others); reports the max over ranks"""
+    from sparsefusion_b200.distillation import Distiller, SceneCache
+    from sparsefusion_b200.imagen_pytorch import Unet
+    from sparsefusion_b200.ldm_autoencoder import AutoencoderKL
+    from sparsefusion_b200.lpips_vgg import PerceptualLoss
+    from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
+    from sparsefusion_b200.synthetic import synthetic_scene
+    from sparsefusion_b200.vldm import DDPM
+    ms, err, calls = float('nan'), None, []
+    try:
+        torch.manual_seed(0)
+        unet = Unet(**UNET_KW)
+        torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)
+        ddpm = DDPM(unets=(unet,), **dict(DDPM_KW, image_sizes=(128,)))
+        torch.nn.init.normal_(ddpm.unets[0].get_parameter('final_conv.weight'), std=0.02)
+        ddpm = ddpm.to(device)
+        vae = AutoencoderKL().to(device).eval()
+        opt = get_default_torch_ngp_opt()
+        opt.w = opt.h = 512
+        ngp = NeRFNetwork(opt)
+        ngp.encoder.embeddings.data.uniform_(-0.5, 0.5)
+        ngp = ngp.to(device).train()
+        scene = SceneCache(**synthetic_scene(n_input=6, n_target=4, image_size=1024, latent=128, render_hw=512, seed=rank)).to(device)
+        dist = Distiller(ngp, vae, ddpm, opt, scene, seed=rank, percep=PerceptualLoss('vgg', device=device, seed=0))
+        thres = [0.13] * warmup + [0.25, 0.49][:steps]          # 26 + 50 UNet evaluations over the two timed steps: mean 38 = the expectation of the reference's draw
+        for i in range(warmup):
+            dist.step(1001 + i, max_thres=thres[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            a, b = dist.step(1001 + warmup + i, max_thres=thres[warmup + i])
+            calls.append(dist.last.get('unet_calls', 0))
+        e1.record()
+        torch.cuda.synchronize()
+        if not (torch.isfinite(a) and torch.isfinite(b)):
+            raise RuntimeError('non-finite loss')
+        ms = e0.elapsed_time(e1) / steps
+        del dist, scene, ngp, vae, ddpm, unet
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        err = f'{type(e).__name__}: {e}'[:300]
+    t = torch.tensor([ms if err is None else -1.0], device=device)
+    if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        torch.distributed.all_gather(gathered, t)
+        allms = [float(g) for g in gathered]
+    else:
+        allms = [float(t)]
+    ok = [m for m in allms if m > 0]
+    out = {'workload': 'BASELINE configs[4] (SURVEY 8d C5): 6 input views, 128x128x4 latents (1024x1024 images, 512x512 rays x 128 samples), one target view per GPU per '
+                       'step, reference iteration on every rank (replicas)', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ranks_ok': len(ok),
+           'unet_evals_per_step_mean': round(float(np.mean(calls)), 2) if calls else None, 'unet_gflop_per_eval': 1004.3}
+    if len(ok) == world:
+        worst = max(ok)
+        out.update({'ms_per_step': round(worst, 1), 'views_per_s': round(world / (worst / 1e3), 4), 'steps_per_s_per_gpu': round(1e3 / worst, 4)})
+    if err is not None:
+        out['error_rank%d' % rank] = err
     return out
 
 
@@ -581,6 +648,8 @@ if __name__ == '__main__':
     ap.add_argument('--no-c4', dest='no_c4', action='store_true', help='skip the fixed 64-view minibatch leg')
     ap.add_argument('--no-c2', dest='no_c2', action='store_true', help='skip the 64-view 256x256 render leg')
     ap.add_argument('--no-gpuref', dest='no_gpuref', action='store_true', help='skip the eager-PyTorch-on-GPU reference leg')
+    ap.add_argument('--c5', action='store_true', help='run the 128x128-latent leg (BASELINE configs[4]); on by default with 8 GPUs')
+    ap.add_argument('--no-c5', dest='no_c5', action='store_true', help='skip it with 8 GPUs')
     ap.add_argument('--views', type=int, default=0, help='target views per optimiser step (view-batched step); default: 1 on one GPU, N on N GPUs')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup

@@ -84,6 +84,8 @@ class _RunRender(torch.autograd.Function):
 
 
 class NeRFRenderer(nn.Module):
+    MAX_RAYS_PER_LAUNCH = 65536      # rays per fused-render autograd node (x 128 samples x 1.4 KB of backward tape = 12 GB transient)
+
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
@@ -158,8 +160,16 @@ class NeRFRenderer(nn.Module):
                 pdf_u = torch.linspace(0. + 0.5 / upsample_steps, 1. - 0.5 / upsample_steps, steps=upsample_steps, device=dev).expand(N, upsample_steps)
             pdf_u = pdf_u.contiguous()
             p = self._field_params()
-            image, depth, ws, nears, fars = _RunRender.apply(self, rays_o, rays_d, aabb, self.min_near, bg_color,
-                                                             None if perturb_noise is None else perturb_noise.contiguous(), pdf_u, *p)
+            pn = None if perturb_noise is None else perturb_noise.contiguous()
+            if N <= self.MAX_RAYS_PER_LAUNCH:
+                image, depth, ws, nears, fars = _RunRender.apply(self, rays_o, rays_d, aabb, self.min_near, bg_color, pn, pdf_u, *p)
+            else:
+                # large images (512x512 rays and up): the backward's activation tapes are 1.4 KB per sample point, so rays go through the fused
+                # kernels in slices -- each slice is its own autograd node, whose tape exists only while that slice back-propagates
+                parts = [_RunRender.apply(self, rays_o[i:i + self.MAX_RAYS_PER_LAUNCH], rays_d[i:i + self.MAX_RAYS_PER_LAUNCH], aabb, self.min_near, bg_color,
+                                          None if pn is None else pn[i:i + self.MAX_RAYS_PER_LAUNCH], pdf_u[i:i + self.MAX_RAYS_PER_LAUNCH], *p)
+                         for i in range(0, N, self.MAX_RAYS_PER_LAUNCH)]
+                image, depth, ws, nears, fars = (torch.cat([q[j] for q in parts]) for j in range(5))
         return {'image': image.view(*prefix, 3), 'depth': depth.view(*prefix), 'weights_sum': ws, 'mask': (nears < fars).reshape(*prefix)}
 
     # ------------------------------------------------------------------------------------------ cuda_ray path
