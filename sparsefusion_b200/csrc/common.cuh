@@ -43,8 +43,10 @@ void phase_bind_conv_v2(unsigned long long* buf, unsigned int cap);
 // optional paths (sfb_set_fusion): bit 0 = NGP MLP weight gradients as tcgen05 GEMMs (off: the SIMT outer-product kernel)
 int fusion_mask();
 static inline bool wgrad_tc_enabled() { return (fusion_mask() & 1) != 0; }
+static inline bool field_v2_enabled() { return (fusion_mask() & 16) != 0; }    // tiled NGP field kernels (128-point GEMM tiles in shared memory, no tape)
 static inline bool gn_grid_enabled() { return (fusion_mask() & 2) != 0; }
-static inline bool gn_cluster_enabled() { return (fusion_mask() & 4) != 0; }   // single-launch GroupNorm: one thread-block cluster per (image, group)
+static inline bool gn_cluster_enabled() { return (fusion_mask() & 4) != 0; }
+static inline bool gn_cluster_adaptive() { return (fusion_mask() & 8) != 0; }  // cluster width by tensor size (1 = a plain CTA per group) instead of always 8   // single-launch GroupNorm: one thread-block cluster per (image, group)
 static inline bool gca_cluster_enabled() { return (fusion_mask() & 8) != 0; }  // GlobalContext + gate + residual as one cluster kernel
 static inline bool gca_cluster_wide() { return (fusion_mask() & 16) != 0; }    // ... with 16-CTA (non-portable) clusters where the slab allows, else 8   // single-launch GroupNorm with a software grid barrier (batch 1)
 #ifdef __CUDACC__

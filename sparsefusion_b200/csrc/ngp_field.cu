@@ -402,6 +402,421 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// ================================================================================================ v2: tiled field kernels
+// Round 2.  The kernels above evaluate the MLP one point per thread: every FMA quartet costs a broadcast LDS.128 of weights plus the activation
+// load, which makes them LSU-bound (forward 193 clk / point / SM, of which the 128 grid gathers are ~128), and the backward writes 1.4 KB / point
+// of activation tapes to HBM for separate weight-gradient GEMMs.  v2 treats a TILE of 128 points as a small GEMM problem per layer:
+//   * activations live feature-major in shared memory ([feature][point], row stride 132 floats) -- E (32), H1, H2 (64 rows) and, in the
+//     backward, D2, D1, D0; a thread owns an 8-output x 8-point register tile (64 accumulators), so one k-step is 2 + 2 LDS.128 for 64 FMA
+//     (the v1 loop: 17 shared-memory loads for 64 FMA);
+//   * the backward accumulates dW / db of the tile IN REGISTERS across the CTA's whole grid-stride loop (per-thread 4x8 / 4x4 tiles of
+//     dW1 / dW0, reduction over the points vectorised 4 wide) and reduces once per CTA -- no tape, no second pass over HBM;
+//   * encode gathers and gradient scatters are issued two levels (16 requests) at a time per thread; index arithmetic is the shared one
+//     (gridencoder.cuh), so rows stay bit-identical to the reference.
+// Bound: LSU (128 gathers + 128 red.v2 per point), then FP32 FMA.
+constexpr int kPT = 128;          // points per tile == threads per CTA
+constexpr int kLd = 132;          // row stride of the activation tiles (floats): rows 4 banks apart -> conflict-free 128-bit row walks
+
+// 2 levels x 8 corners of one point: rows and interpolation weights
+struct Corner2 {
+    uint32_t row[16];
+    float w[16];
+    uint32_t off[2];
+};
+__device__ __forceinline__ void locate_2levels(const float (&u)[3], uint32_t level0, const int32_t* __restrict__ offsets, const FieldGeom& g, Corner2& c) {
+#pragma unroll
+    for (uint32_t l = 0; l < 2; ++l) {
+        const GridLevel lv = grid_level(level0 + l, g.S, g.H, offsets);
+        c.off[l] = lv.offset;
+        float frac[3];
+        uint32_t cell[3];
+        grid_locate<3>(u, lv.scale, false, frac, cell);
+#pragma unroll
+        for (uint32_t corner = 0; corner < 8; ++corner) {
+            float w = 1.f;
+            uint32_t cl[3];
+#pragma unroll
+            for (uint32_t d = 0; d < 3; ++d) {
+                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; cl[d] = cell[d]; }
+                else { w *= frac[d]; cl[d] = cell[d] + 1; }
+            }
+            c.row[l * 8 + corner] = grid_row<3>(1u, false, lv.rows, lv.resolution, cl);
+            c.w[l * 8 + corner] = w;
+        }
+    }
+}
+
+// encode one point into column `col` of E ([32][kLd]); the accumulation order per level equals encode_point's (corner 0..7)
+__device__ __forceinline__ void encode_point_tile(const float (&x)[3], bool valid, const float* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                  const FieldGeom& g, float* __restrict__ E, int col) {
+    float u[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(__fadd_rn(x[d], g.bound), 2 * g.bound);  // grid.py:142
+    const bool live = valid && !grid_out_of_range<3>(u);
+#pragma unroll 1
+    for (uint32_t level = 0; level < kL; level += 2) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            Corner2 c;
+            locate_2levels(u, level, offsets, g, c);
+            float2 v[16];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                // corners 2m / 2m+1 differ in x only: their rows are neighbours unless the level's index wraps between them; an even first row makes
+                // the pair one aligned 16-byte element (level offsets are multiples of 8 rows) -> one request instead of two for ~half of the pairs
+                const int i0 = 2 * m, i1 = i0 + 1;
+                const float* base = table + (size_t)c.off[m >> 2] * kC;
+                if (c.row[i1] == c.row[i0] + 1u && (c.row[i0] & 1u) == 0u) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(base) + (c.row[i0] >> 1));
+                    v[i0] = make_float2(t.x, t.y);
+                    v[i1] = make_float2(t.z, t.w);
+                } else {
+                    v[i0] = __ldg(reinterpret_cast<const float2*>(base) + c.row[i0]);
+                    v[i1] = __ldg(reinterpret_cast<const float2*>(base) + c.row[i1]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                a[(i >> 3) * 2] += c.w[i] * v[i].x;
+                a[(i >> 3) * 2 + 1] += c.w[i] * v[i].y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) E[(2 * level + q) * kLd + col] = a[q];
+    }
+}
+
+// Out[j][p] = epi(bias[j] + sum_k WT[k][j] * A[k][p]) for a 64-output x 128-point tile; WT is [K][64] (reduction index major), A and Out are
+// [.][kLd].  128 threads: thread (tp = t & 15, tj = t >> 4) owns outputs 8 tj .. 8 tj + 7 of points {4 tp .. 4 tp + 3} u {64 + 4 tp .. 64 + 4 tp + 3}.
+// EPI: 0 = ReLU, 1 = multiply by (G[j][p] > 0) (ReLU backward through the activation G)
+template <int K, int EPI>
+__device__ __forceinline__ void dense_tile64(const float* __restrict__ WT, const float* __restrict__ bias, const float* __restrict__ A,
+                                             float* __restrict__ Out, const float* __restrict__ G) {
+    const int tp = threadIdx.x & 15, tj = threadIdx.x >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float b = bias ? bias[tj * 8 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = b;
+    }
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLd + tp * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLd + 64 + tp * 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(WT + k * kHid + tj * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(WT + k * kHid + tj * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] += w[j] * a[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int row = (tj * 8 + j) * kLd;
+        float o[8];
+        if (EPI == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaxf(acc[j][i], 0.f);
+        } else {
+            const float4 g0 = *reinterpret_cast<const float4*>(G + row + tp * 4);
+            const float4 g1 = *reinterpret_cast<const float4*>(G + row + 64 + tp * 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = gg[i] > 0.f ? acc[j][i] : 0.f;
+        }
+        *reinterpret_cast<float4*>(Out + row + tp * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(Out + row + 64 + tp * 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// D0[k][p] = sum_j W0[j][k] * D1[j][p]: 32 outputs x 128 points, reduction over 64; W0 row-major [64][32].  Thread (tp = t & 15, tk = t >> 4) owns
+// outputs 4 tk .. 4 tk + 3 of the same 8 points as above.
+__device__ __forceinline__ void dense_tile32(const float* __restrict__ W0, const float* __restrict__ A, float* __restrict__ Out) {
+    const int tp = threadIdx.x & 15, tk = threadIdx.x >> 4;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < kHid; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLd + tp * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLd + 64 + tp * 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(W0 + k * kIn + tk * 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float w[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] += w[j] * a[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int row = (tk * 4 + j) * kLd;
+        *reinterpret_cast<float4*>(Out + row + tp * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        *reinterpret_cast<float4*>(Out + row + 64 + tp * 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+    }
+}
+
+// acc[jr][r] += sum_p D[j0 + jr][p] * H[tk + 8 r][p] over the tile's 128 points (4 at a time): the thread's share of dW = D H^T.
+// Thread (tk = t & 7, tj = t >> 3): rows j0 = 4 tj of D, rows {tk, tk + 8, ...} (NR of them) of H -- a quarter-warp walks 8 consecutive H rows
+// (conflict-free with the 132-float stride) and shares its D rows (broadcast).
+template <int NR>
+__device__ __forceinline__ void wgrad_tile(const float* __restrict__ D, const float* __restrict__ H, float (&acc)[4][NR]) {
+    const int tk = threadIdx.x & 7, tj = threadIdx.x >> 3;
+#pragma unroll 2
+    for (int p = 0; p < kPT; p += 4) {
+        float4 d[4], h[NR];
+#pragma unroll
+        for (int jr = 0; jr < 4; ++jr) d[jr] = *reinterpret_cast<const float4*>(D + (tj * 4 + jr) * kLd + p);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) h[r] = *reinterpret_cast<const float4*>(H + (tk + 8 * r) * kLd + p);
+#pragma unroll
+        for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[jr][r] += (d[jr].x * h[r].x + d[jr].y * h[r].y) + (d[jr].z * h[r].z + d[jr].w * h[r].w);
+    }
+}
+
+struct FieldSmemV2 {
+    float WT0[kIn * kHid];    // [k][j]  forward layer 0
+    float WT1[kHid * kHid];   // [k][j]  forward layer 1
+    float WT2[kHid * kOut];   // [k][c]  forward layer 2 and D2 = W2^T d3
+    float b0[kHid], b1[kHid], b2[kOut];
+};
+struct FieldSmemV2Bwd {
+    FieldSmemV2 f;
+    float W1[kHid * kHid];    // [j][k] row-major (as stored): D1 = W1^T D2
+    float W0[kHid * kIn];     // [j][k] row-major: D0 = W0^T D1
+    float d3[kOut * kLd];     // output-layer gradients of the tile, feature-major
+};
+
+__device__ __forceinline__ void load_weights_v2(FieldSmemV2& s, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                                                const float* b2) {
+    for (int i = threadIdx.x; i < kHid * kIn; i += blockDim.x) { const int j = i / kIn, k = i - j * kIn; s.WT0[k * kHid + j] = W0[i]; }
+    for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x) { const int j = i / kHid, k = i - j * kHid; s.WT1[k * kHid + j] = W1[i]; }
+    for (int i = threadIdx.x; i < kOut * kHid; i += blockDim.x) { const int j = i / kHid, k = i - j * kHid; s.WT2[k * kOut + j] = W2[i]; }
+    for (int i = threadIdx.x; i < kHid; i += blockDim.x) { s.b0[i] = b0[i]; s.b1[i] = b1[i]; }
+    if (threadIdx.x < kOut) s.b2[threadIdx.x] = b2[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPT) field_forward_v2_kernel(PointSource ps, uint32_t B, const float* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                              FieldGeom g, const float* __restrict__ W0, const float* __restrict__ b0,
+                                                              const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                                                              const float* __restrict__ b2, float* __restrict__ sigma, float* __restrict__ rgb) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    FieldSmemV2& s = *reinterpret_cast<FieldSmemV2*>(smraw);
+    float* bufA = reinterpret_cast<float*>(smraw + sizeof(FieldSmemV2));      // E (rows 0..31), then H2
+    float* bufB = bufA + kHid * kLd;                                         // H1
+    load_weights_v2(s, W0, b0, W1, b1, W2, b2);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const uint32_t tiles = (B + kPT - 1) / kPT;
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t p = tile * kPT + tid;
+        const bool valid = p < B;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) fetch_point(ps, p, x);
+        encode_point_tile(x, valid, table, offsets, g, bufA, tid);
+        __syncthreads();
+        dense_tile64<kIn, 0>(s.WT0, s.b0, bufA, bufB, nullptr);
+        __syncthreads();
+        dense_tile64<kHid, 0>(s.WT1, s.b1, bufB, bufA, nullptr);
+        __syncthreads();
+        if (valid) {
+            float o0 = s.b2[0], o1 = s.b2[1], o2 = s.b2[2], o3 = s.b2[3];
+#pragma unroll 8
+            for (int k = 0; k < kHid; ++k) {
+                const float hk = bufA[k * kLd + tid];
+                const float4 w = *reinterpret_cast<const float4*>(s.WT2 + k * kOut);
+                o0 += w.x * hk; o1 += w.y * hk; o2 += w.z * hk; o3 += w.w * hk;
+            }
+            sigma[p] = expf(o0 + density_blob(x));
+            if (rgb) {
+                rgb[(size_t)p * 3] = 1.f / (1.f + expf(-o1));
+                rgb[(size_t)p * 3 + 1] = 1.f / (1.f + expf(-o2));
+                rgb[(size_t)p * 3 + 2] = 1.f / (1.f + expf(-o3));
+            }
+        }
+        __syncthreads();     // bufA is overwritten by the next tile's encode
+    }
+}
+
+__global__ void __launch_bounds__(kPT, 1) field_backward_v2_kernel(PointSource ps, uint32_t B, const float* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                                  FieldGeom g, const float* __restrict__ W0, const float* __restrict__ b0,
+                                                                  const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                  const float* __restrict__ b2, const float* __restrict__ g_sigma,
+                                                                  const float* __restrict__ g_rgb, float* __restrict__ grad_table, float* __restrict__ gW0,
+                                                                  float* __restrict__ gb0, float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                  float* __restrict__ gW2, float* __restrict__ gb2) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    FieldSmemV2Bwd& s = *reinterpret_cast<FieldSmemV2Bwd*>(smraw);
+    float* bufA = reinterpret_cast<float*>(smraw + sizeof(FieldSmemV2Bwd));   // E rows 0..31 | D0 rows 32..63
+    float* bufB = bufA + kHid * kLd;                                          // H1
+    float* bufC = bufB + kHid * kLd;                                          // H2, then D1
+    float* bufD = bufC + kHid * kLd;                                          // D2
+    load_weights_v2(s.f, W0, b0, W1, b1, W2, b2);
+    for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x) s.W1[i] = W1[i];
+    for (int i = threadIdx.x; i < kHid * kIn; i += blockDim.x) s.W0[i] = W0[i];
+    __syncthreads();
+    const int tid = threadIdx.x;
+    // per-thread shares of the weight gradients, kept in registers over all tiles of this CTA
+    float aW1[4][8], aW0[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) aW1[a][r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) aW0[a][r] = 0.f;
+    }
+    float aW2[2] = {0.f, 0.f};      // dW2[c][k]: k = tid & 63, c = 2 (tid >> 6) + {0, 1}
+    float ab = 0.f;                 // bias share: tid < 64: db1[tid]; tid >= 64: db0[tid - 64]
+    float ab2 = 0.f;                // tid < 4: db2[tid]
+    const uint32_t tiles = (B + kPT - 1) / kPT;
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t p = tile * kPT + tid;
+        const bool valid = p < B;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) fetch_point(ps, p, x);
+        // ---- forward recompute: E -> H1 -> H2
+        encode_point_tile(x, valid, table, offsets, g, bufA, tid);
+        __syncthreads();
+        dense_tile64<kIn, 0>(s.f.WT0, s.f.b0, bufA, bufB, nullptr);
+        __syncthreads();
+        dense_tile64<kHid, 0>(s.f.WT1, s.f.b1, bufB, bufC, nullptr);
+        __syncthreads();
+        // ---- output layer and its gradient (thread = point), then D2 = relu'(H2) (W2^T d3)
+        float d3[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+            float o[4] = {s.f.b2[0], s.f.b2[1], s.f.b2[2], s.f.b2[3]};
+#pragma unroll 8
+            for (int k = 0; k < kHid; ++k) {
+                const float hk = bufC[k * kLd + tid];
+                const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
+                o[0] += w.x * hk; o[1] += w.y * hk; o[2] += w.z * hk; o[3] += w.w * hk;
+            }
+            const float pre = o[0] + density_blob(x);
+            d3[0] = g_sigma[p] * expf(fminf(fmaxf(pre, -15.f), 15.f));       // trunc_exp backward (ngp_activation.py:19-21)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sg = 1.f / (1.f + expf(-o[c + 1]));
+                d3[c + 1] = g_rgb ? g_rgb[(size_t)p * 3 + c] * sg * (1.f - sg) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s.d3[c * kLd + tid] = d3[c];
+#pragma unroll 8
+        for (int k = 0; k < kHid; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
+            const float v = w.x * d3[0] + w.y * d3[1] + w.z * d3[2] + w.w * d3[3];
+            bufD[k * kLd + tid] = bufC[k * kLd + tid] > 0.f ? v : 0.f;
+        }
+        __syncthreads();
+        // ---- dW2 += d3 H2^T, db2, db1 (D2 row sums)
+        {
+            const int k = tid & 63, c0 = (tid >> 6) * 2;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < kPT; q += 4) {
+                const float4 h = *reinterpret_cast<const float4*>(bufC + k * kLd + q);
+                const float4 da = *reinterpret_cast<const float4*>(s.d3 + c0 * kLd + q);
+                const float4 db = *reinterpret_cast<const float4*>(s.d3 + (c0 + 1) * kLd + q);
+                s0 += (da.x * h.x + da.y * h.y) + (da.z * h.z + da.w * h.w);
+                s1 += (db.x * h.x + db.y * h.y) + (db.z * h.z + db.w * h.w);
+            }
+            aW2[0] += s0; aW2[1] += s1;
+            if (tid < 64) {
+                float t = 0.f;
+#pragma unroll 4
+                for (int q = 0; q < kPT; q += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(bufD + tid * kLd + q);
+                    t += (v.x + v.y) + (v.z + v.w);
+                }
+                ab += t;
+            }
+            if (tid >= 64 && tid < 68) {
+                float t = 0.f;
+                for (int q = 0; q < kPT; q += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(s.d3 + (tid - 64) * kLd + q);
+                    t += (v.x + v.y) + (v.z + v.w);
+                }
+                ab2 += t;
+            }
+        }
+        __syncthreads();     // every reader of H2 (bufC) is done before D1 overwrites it
+        // ---- D1 = relu'(H1) (W1^T D2) -> bufC ; dW1 += D2 H1^T
+        dense_tile64<kHid, 1>(s.W1, nullptr, bufD, bufC, bufB);
+        wgrad_tile<8>(bufD, bufB, aW1);
+        __syncthreads();
+        // ---- D0 = W0^T D1 -> bufA rows 32..63 ; dW0 += D1 E^T ; db0
+        dense_tile32(s.W0, bufC, bufA + kIn * kLd);
+        wgrad_tile<4>(bufC, bufA, aW0);
+        if (tid >= 64) {
+            float t = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < kPT; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(bufC + (tid - 64) * kLd + q);
+                t += (v.x + v.y) + (v.z + v.w);
+            }
+            ab += t;
+        }
+        __syncthreads();
+        // ---- scatter D0 into the embedding gradient (kernel_grid_backward, gridencoder.cu:226-313), two levels per batch
+        if (valid) {
+            float u[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(__fadd_rn(x[d], g.bound), 2 * g.bound);
+            if (!grid_out_of_range<3>(u)) {
+#pragma unroll 1
+                for (uint32_t level = 0; level < kL; level += 2) {
+                    Corner2 c;
+                    locate_2levels(u, level, offsets, g, c);
+                    float gq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gq[q] = bufA[(kIn + 2 * level + q) * kLd + tid];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int i0 = 2 * m, i1 = i0 + 1;
+                        float* base = grad_table + (size_t)c.off[m >> 2] * kC;
+                        const float g0 = gq[(m >> 2) * 2], g1 = gq[(m >> 2) * 2 + 1];
+                        if (c.row[i1] == c.row[i0] + 1u && (c.row[i0] & 1u) == 0u) {      // neighbouring rows, 16-byte aligned: one vector reduction
+                            float* q = base + (size_t)c.row[i0] * kC;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(c.w[i0] * g0), "f"(c.w[i0] * g1), "f"(c.w[i1] * g0),
+                                         "f"(c.w[i1] * g1)
+                                         : "memory");
+                        } else {
+                            const float wa[2] = {c.w[i0] * g0, c.w[i0] * g1}, wb[2] = {c.w[i1] * g0, c.w[i1] * g1};
+                            grid_red_add_row<2>(base, c.row[i0], wa);
+                            grid_red_add_row<2>(base, c.row[i1], wb);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();     // bufA / bufB / bufC / bufD are rewritten by the next tile
+    }
+    // ---- one reduction per CTA
+    {
+        const int tk = tid & 7, tj = tid >> 3;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) atomicAdd(gW1 + (size_t)(tj * 4 + a) * kHid + tk + 8 * r, aW1[a][r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) atomicAdd(gW0 + (size_t)(tj * 4 + a) * kIn + tk + 8 * r, aW0[a][r]);
+        }
+        const int k = tid & 63, c0 = (tid >> 6) * 2;
+        atomicAdd(gW2 + (size_t)c0 * kHid + k, aW2[0]);
+        atomicAdd(gW2 + (size_t)(c0 + 1) * kHid + k, aW2[1]);
+        if (tid < 64) atomicAdd(gb1 + tid, ab);
+        else atomicAdd(gb0 + (tid - 64), ab);
+        if (tid >= 64 && tid < 68) atomicAdd(gb2 + (tid - 64), ab2);
+    }
+}
+
 static int field_args_ok(const float* table, const int32_t* offsets, const float* W0, const float* b0, const float* W1, const float* b1,
                          const float* W2, const float* b2) {
     return table && offsets && W0 && b0 && W1 && b1 && W2 && b2;
@@ -427,6 +842,15 @@ int sfb_ngp_field_forward(const float* xyz, const float* rays_o, const float* ra
     SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && sigma, "ngp_field_forward: null pointer");
     SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_forward: give xyz or (rays_o, rays_d, z, T)");
     if (B == 0) return SFB_OK;
+    if (field_v2_enabled()) {
+        const size_t smem2 = sizeof(FieldSmemV2) + (size_t)2 * kHid * kLd * 4;
+        SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_forward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)));
+        const uint32_t tiles = ceil_div(B, (uint32_t)kPT);
+        const uint32_t blocks2 = min(tiles, (uint32_t)sm_count() * 2);
+        field_forward_v2_kernel<<<blocks2, kPT, smem2, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
+                                                                           FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, sigma, rgb);
+        return check_launch("ngp_field_forward(v2)");
+    }
     const size_t smem = sizeof(FieldSmem) + (size_t)kHid * kFieldThreads * 4;
     SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     const uint32_t blocks = min(ceil_div(B, (uint32_t)kFieldThreads), (uint32_t)sm_count() * 3);
@@ -444,10 +868,21 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
                            void* stream) {
     if (B == 0) return SFB_OK;
     SFB_REQUIRE(field_args_ok(embeddings, offsets, W0, b0, W1, b1, W2, b2) && grad_sigma && grad_embeddings && gW0 && gb0 && gW1 && gb1 && gW2 &&
-                    gb2 && tape,
+                    gb2 && (tape || field_v2_enabled()),
                 "ngp_field_backward: null pointer");
     SFB_REQUIRE(xyz || (rays_o && rays_d && z && T > 0), "ngp_field_backward: give xyz or (rays_o, rays_d, z, T)");
     if (B == 0) return SFB_OK;
+    if (field_v2_enabled()) {
+        // tiled kernel: activations stay in shared memory, weight gradients accumulate in registers per CTA -- `tape` is not touched
+        const size_t smem2 = sizeof(FieldSmemV2Bwd) + (size_t)4 * kHid * kLd * 4;
+        SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_backward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)));
+        const uint32_t tiles = ceil_div(B, (uint32_t)kPT);
+        const uint32_t blocks2 = min(tiles, (uint32_t)sm_count());
+        field_backward_v2_kernel<<<blocks2, kPT, smem2, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
+                                                                            FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, grad_sigma, grad_rgb,
+                                                                            grad_embeddings, gW0, gb0, gW1, gb1, gW2, gb2);
+        return check_launch("ngp_field_backward(v2)");
+    }
     const uint32_t Bp = sfb_ngp_field_tape_points(B);
     float* H0 = tape;
     float* H1 = H0 + (size_t)kIn * Bp;
@@ -488,6 +923,7 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
 }
 
 uint64_t sfb_ngp_field_tape_floats(uint32_t B) {
+    if (field_v2_enabled()) return 0;      // the tiled backward keeps every activation in shared memory
     return (uint64_t)sfb_ngp_field_tape_points(B) * (kIn + 4 * kHid + kOut);
 }
 

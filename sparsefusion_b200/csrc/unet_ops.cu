@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(256) gn_cluster_kernel(const float* __restrict
             stat = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
         }
     }
-    cl.sync();                                             // nobody reads a peer's shared memory after this point (safe to exit), stat visible
+    __syncthreads();                                       // stat visible to the CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // this CTA has finished reading its peers' shared memory ...
     const float2 st = stat;
     float* yb = y + ((int64_t)n * HW + p0) * ldy + g * Cg;
 #pragma unroll
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(256) gn_cluster_kernel(const float* __restrict
             *reinterpret_cast<float4*>(yb + (int64_t)pix * ldy + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // ... and does not exit before every peer has finished reading its own
 }
 
 // y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ), rounded to tf32.  film [NB, 2C] (scale | shift) or null.  grid (blocks, NB)
@@ -876,6 +878,12 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
         // one cluster of k CTAs per (image, group); a CTA holds ceil(HW/k) * Cg/4 float4 in registers.  Cg >= 16 keeps every pixel's share a
         // multiple of 64 contiguous bytes (full sectors); narrower groups (the VAE's 128-channel layers) stay on the row-coalesced two-launch path
         unsigned k = 8;
+        if (gn_cluster_adaptive()) {
+            // few pixels (the 16x16 / 8x8 / 4x4 stages): a narrower cluster -- or a plain CTA per group -- has less to synchronise; target ~4 float4 per thread
+            const int64_t per_group = (int64_t)HW * (Cg / 4);
+            k = 1;
+            while (k < 8 && per_group > (int64_t)k * 1024) k <<= 1;
+        }
         while (k > 1 && (int)k > HW) k >>= 1;
         const int64_t per_cta = (int64_t)((HW + (int)k - 1) / (int)k) * (Cg / 4);
         const int items = (int)((per_cta + 255) / 256);

@@ -39,9 +39,10 @@ def test_state_dict_keys_match_reference_checkpoint_layout():
     assert {'density_grid', 'density_bitfield', 'step_counter'} <= set(net2.state_dict().keys())
 
 
-@pytest.fixture(params=[0x7fffffff, 0], ids=['wgrad-tcgen05', 'wgrad-simt'])
+@pytest.fixture(params=[0x7fffffff, 0x7fffffff & ~16, 0], ids=['field-v2-tiled', 'field-v1-wgrad-tcgen05', 'field-v1-wgrad-simt'])
 def wgrad_path(request):
-    """both implementations of the MLP weight gradients (sfb_set_fusion bit 0)"""
+    """the three implementations of the field kernels: v2 = 128-point GEMM tiles in shared memory with in-register weight gradients (default,
+    sfb_set_fusion bit 4); v1 = one point per thread + activation tapes, with the weight gradients as tcgen05 GEMMs (bit 0) or a SIMT outer product"""
     from sparsefusion_b200 import _lib as lib
     lib.call('sfb_set_fusion', request.param)
     yield request.param
@@ -72,6 +73,14 @@ def test_field_forward_backward_vs_oracle(wgrad_path):
         assert r < 2e-3, (k, r)
     # density() is the same function; empty input is fine
     assert net.density(torch.zeros(0, 3, device='cuda'))['sigma'].shape == (0,)
+    # ragged tile: a point count that is not a multiple of the 128-point tile, against the one-point-per-thread kernel
+    from sparsefusion_b200 import _lib as lib
+    xs = torch.from_numpy(x[:1237]).cuda()
+    s_cur, c_cur = net.common_forward(xs)
+    lib.call('sfb_set_fusion', 0x7fffffff & ~16)
+    s_v1, c_v1 = net.common_forward(xs)
+    lib.call('sfb_set_fusion', wgrad_path)
+    assert _rel(s_cur, s_v1) < 1e-6 and _rel(c_cur, c_v1) < 1e-6
 
 
 def test_run_render_vs_oracle_and_golden(golden_dir):

@@ -50,15 +50,18 @@ def unet_bench(out):
         _lib.call('sfb_set_pdl', 0)
     if 'nofuse' in sys.argv:
         _lib.call('sfb_set_fusion', 0)
+    for a in sys.argv:
+        if a.startswith('fuse='):
+            _lib.call('sfb_set_fusion', int(a[5:], 0))
     from sparsefusion_b200.imagen_pytorch import Unet, UnetGraph
     unet = Unet(channels=4, dim=256, dim_mults=(1, 2, 4, 4), num_resnet_blocks=(2, 2, 2, 2), layer_attns=(False, False, False, True),
                 layer_cross_attns=(False,) * 4, cond_images_channels=256, attn_pool_text=False, cond_on_z=False, conditional_embed_dim=None).cuda()
     torch.nn.init.normal_(unet.get_parameter('final_conv.weight'), std=0.02)
     out['unet'] = {}
-    for mode in ('tf32x3', 'tf32'):
+    for mode in (('tf32x3',) if 'x3only' in sys.argv else ('tf32x3', 'tf32')):
         ops.set_precision(mode)
         unet.prepare()
-        for nb in (1, 8):
+        for nb in ((1, 8, 16) if 'nb16' in sys.argv else (1, 8)):
             x, cond, t = torch.randn(nb, 4, 32, 32, device='cuda'), torch.randn(nb, 256, 32, 32, device='cuda'), torch.full((nb,), 0.3, device='cuda')
             eager = timeit(lambda: unet.forward(x, t, cond_images=cond), iters=5, warmup=2, flush=False)
             runner = UnetGraph(unet)
@@ -248,6 +251,10 @@ def vae_bench(out):
 
 def render_bench(out):
     import numpy as np
+    from sparsefusion_b200 import _lib
+    for a in sys.argv:
+        if a.startswith('fuse='):
+            _lib.call('sfb_set_fusion', int(a[5:], 0))
     from sparsefusion_b200.network_grid import NeRFNetwork, get_default_torch_ngp_opt
     opt = get_default_torch_ngp_opt()
     net = NeRFNetwork(opt).cuda().train()

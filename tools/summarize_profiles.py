@@ -16,9 +16,9 @@ KEEP = [('gpu__time_duration.sum', 'duration_us'), ('dram__bytes_read.sum', 'dra
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occupancy_pct'), ('launch__registers_per_thread', 'registers'),
         # tensor pipe: what the north star asks the captures to report next to the HBM numbers (`--set full` collects the first two; the explicit
         # --metrics pass of tools/gpu_profile_r2.sh adds the others where the tool exposes them for sm_100)
-        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_pipe_pct'),
+        ('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor_pipe_pct'),
         ('sm__inst_executed_pipe_tensor.sum', 'tensor_inst'),
-        ('sm__pipe_tensor_subpipe_tcgen05_cycles_active.avg.pct_of_peak_sustained_active', 'tcgen05_pipe_pct'),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_pipe_active_pct'),
         ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram_throughput_pct')]
 SCALE = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
 
