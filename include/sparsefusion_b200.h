@@ -186,12 +186,16 @@ int sfb_nhwc_to_nchw(const float* src, float* dst, int NB, int C, int H, int W, 
 /* torch.cat((x, skip * scale), dim=1) of the up path (:1639) */
 int sfb_concat2_nhwc(const float* a, int C1, int64_t lda, const float* b, int C2, int64_t ldb, float scale_b, float* out, int64_t ldo,
                      int64_t npix, void* stream);
+/* im2col of a 4-channel NHWC tensor (16-byte pixels): out[pixel][(ky*KW + kx)*4 + c] = x[pixel + (ky - pad, kx - pad)][c], zero outside and in the
+ * tail up to ldo.  Turns the 4-latent-channel share of the CrossEmbed init convolutions (3x3 | 7x7 | 15x15, imagen_pytorch.py:1017-1042) into one
+ * 1x1 convolution with K = 900 instead of three implicit GEMMs padded to 32 channels per tap. */
+int sfb_im2col4_nhwc(const float* x, int64_t ldx, float* out, int64_t ldo, int NB, int H, int W, int KH, int KW, int pad, void* stream);
 /* nn.SiLU + nn.PixelShuffle(2) of PixelShuffleUpsample (:588-592): y [NB,H,W,4*Co] -> out [NB,2H,2W,ldo] */
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
 /* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
  * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch (fp64 partial statistics per pixel slab).
- * Groups of >= 16 channels whose per-CTA slab fits the register file: ONE launch, one thread-block cluster of <= 8 CTAs per (image, group), partial
- * sums exchanged through distributed shared memory (any batch size).  Otherwise two launches (row-coalesced statistics kernel + apply kernel).
+ * Groups of >= 16 channels, batches of <= 4 images, per-CTA slab within the register file: ONE launch, one thread-block cluster of <= 8 CTAs per
+ * (image, group), partial sums exchanged through distributed shared memory.  Otherwise two launches (row-coalesced statistics kernel + apply kernel).
  * counters: unused since ABI 3 (round 1's single-launch variant met at a software grid barrier through these words); pass NULL.
  * Output is TF32-rounded in single-pass mode (it feeds the conv). */
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,

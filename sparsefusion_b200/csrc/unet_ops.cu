@@ -111,6 +111,31 @@ __global__ void pixel_shuffle_silu_kernel(const float* __restrict__ y, float* __
     }
 }
 
+// im2col of a FEW-channel NHWC tensor: out[n][h][w][(ky*KW + kx)*C + c] = x[n][h + ky - pad][w + kx - pad][c] (zero outside), row stride ldo >= KH*KW*C
+// (the tail up to ldo is zero-filled).  The CrossEmbed init convolutions of the UNet see 4 latent channels next to the cached 256-channel share
+// (Unet.precompute_cond): as implicit GEMMs their 32-channel K granularity would spend 8x the work on zero padding (15x15 x 32 instead of 15x15 x 4);
+// unfolded, the three kernel sizes become ONE 1x1 convolution with K = 900.  One thread per (pixel, tap): C <= 4 channels as one float4.
+__global__ void im2col_small_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int H, int W, int C, int KH, int KW,
+                                    int pad, int64_t total) {
+    pdl_sync();
+    const int taps = KH * KW;
+    const int cols = (int)(ldo / 4);                 // float4 columns per output row (taps first, then zero padding)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % cols);
+        int64_t r = i / cols;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < taps) {
+            const int ky = t / KW, kx = t - ky * KW;
+            const int ih = h + ky - pad, iw = w + kx - pad;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)n * H + ih) * W + iw) * ldx));
+        }
+        *reinterpret_cast<float4*>(out + (((int64_t)n * H + h) * W + w) * ldo + (int64_t)t * 4) = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------ GroupNorm
 // Two launches, no atomics: (1) CTAs (group, n, pixel-slab) write fp64 partial (sum, sumsq) per slab; (2) every CTA of the apply kernel
 // folds the <= 64 partials of its image's groups into (mean, rstd) in shared memory (one warp per group) and normalises its pixels.
@@ -862,6 +887,15 @@ int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W
     return check_launch("pixel_shuffle_silu");
 }
 
+int sfb_im2col4_nhwc(const float* x, int64_t ldx, float* out, int64_t ldo, int NB, int H, int W, int KH, int KW, int pad, void* stream) {
+    SFB_REQUIRE(x && out, "im2col4: null pointer");
+    SFB_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldo >= (int64_t)KH * KW * 4, "im2col4: 4-channel input (16-byte pixels), ldo >= 4 KH KW, multiples of 4");
+    const int64_t total = (int64_t)NB * H * W * (ldo / 4);
+    if (total == 0) return SFB_OK;
+    SFB_LAUNCH(im2col_small_kernel, ew_blocks(total), 256, 0, as_stream(stream), x, ldx, out, ldo, H, W, 4, KH, KW, pad, total);
+    return check_launch("im2col4");
+}
+
 int sfb_groupnorm_ws_floats(int NB, int G) { return ((2 * NB * G + 3) / 4) * 4 + NB * G * kGnMaxSlabs * 4; }
 
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
@@ -874,16 +908,13 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     SFB_REQUIRE(G <= kGnMaxGroups, "groupnorm_nhwc: at most 32 groups");
     double2* partial = reinterpret_cast<double2*>(stats_ws + (((size_t)2 * NB * G + 3) / 4) * 4);
     const int C4 = C / 4, Cg = C / G;
-    if (gn_cluster_enabled() && (Cg % 16 == 0) && HW >= 1) {
+    // ... for batches up to 4 images (<= 256 CTAs): it is a latency optimisation.  From batch 8 on the two-launch path's row-coalesced passes win
+    // (batch-16 evaluation 5.87 ms against 6.38 ms)
+    if (gn_cluster_enabled() && (Cg % 16 == 0) && HW >= 1 && NB <= 4) {
         // one cluster of k CTAs per (image, group); a CTA holds ceil(HW/k) * Cg/4 float4 in registers.  Cg >= 16 keeps every pixel's share a
         // multiple of 64 contiguous bytes (full sectors); narrower groups (the VAE's 128-channel layers) stay on the row-coalesced two-launch path
+        // always the widest portable cluster: narrower clusters (or a plain CTA per group) for the small stages measured slower (6.96 vs 5.98 us per launch)
         unsigned k = 8;
-        if (gn_cluster_adaptive()) {
-            // few pixels (the 16x16 / 8x8 / 4x4 stages): a narrower cluster -- or a plain CTA per group -- has less to synchronise; target ~4 float4 per thread
-            const int64_t per_group = (int64_t)HW * (Cg / 4);
-            k = 1;
-            while (k < 8 && per_group > (int64_t)k * 1024) k <<= 1;
-        }
         while (k > 1 && (int)k > HW) k >>= 1;
         const int64_t per_cta = (int64_t)((HW + (int)k - 1) / (int)k) * (Cg / 4);
         const int items = (int)((per_cta + 255) / 256);

@@ -248,6 +248,16 @@ def nhwc_to_nchw(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def im2col4(x: torch.Tensor, kh: int, kw: int, pad: int) -> torch.Tensor:
+    """[NB,H,W,4] -> [NB,H,W,ceil32(4*kh*kw)] patches (tap-major, channel-minor), zero outside the image and in the padding columns"""
+    nb, h, w, c, ldx = _nhwc_meta(x)
+    assert c == 4
+    k = (4 * kh * kw + 31) // 32 * 32
+    out = torch.empty(nb, h, w, k, dtype=torch.float32, device=x.device)
+    lib.call('sfb_im2col4_nhwc', x.data_ptr(), ldx, out.data_ptr(), k, nb, h, w, kh, kw, pad, lib.stream())
+    return out
+
+
 def concat2(a: torch.Tensor, b: torch.Tensor, scale_b: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb, h, w, c1, lda = _nhwc_meta(a)
     _, _, _, c2, ldb = _nhwc_meta(b)
