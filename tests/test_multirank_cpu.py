@@ -91,3 +91,61 @@ def test_single_rank_is_the_reference_choice():
     assert opt.sync_grads(1, None) == 1.0 and float(opt.grad[0]) == 3.0            # no collective when world_size == 1
     with pytest.raises(RuntimeError):                                               # the Adam kernel is CUDA-only: loud on CPU
         opt.step()
+
+
+def _mb_worker(rank, world, store_path, out_dir):
+    """host logic of the view-batched step on R gloo ranks: same permutation stream, disjoint shards covering the step's V views, per-view seeds that do
+    not depend on the rank, photometric term owned by exactly one rank, and ONE all-reduce of the flat buffer per step"""
+    from sparsefusion_b200.distillation import shard_views, step_views, view_seed
+    dist.init_process_group('gloo', init_method=f'file://{store_path}', rank=rank, world_size=world)
+    try:
+        net = _TinyField()
+        opt = FlatAdam(net, lr=5e-4)
+        gen = torch.Generator().manual_seed(0)
+        rec = []
+        n_coll = 0
+        for itr in range(1001, 1004):
+            idx = int(torch.randperm(2, generator=gen)[0])
+            perm = torch.randperm(7, generator=gen)
+            torch.rand(1, generator=gen)
+            views = step_views(perm, 4)
+            mine = shard_views(views, rank, world)
+            opt.zero_grad()
+            if itr % world == rank:                                   # the photometric term: one owner per iteration
+                net(torch.tensor([idx, idx + 1]), torch.full((4,), 0.5)).backward()
+            for v in mine:                                            # mean over the step's V views
+                (net(torch.tensor([v, v + 3]), torch.full((4,), 1.0 + v)) / 4).backward()
+            local = opt.grad.clone()
+            opt.sync_grads(world, None)
+            n_coll += 1
+            rec.append(dict(views=views, mine=mine, owner=itr % world == rank, local=local, summed=opt.grad.clone(),
+                            seeds=[view_seed(11, itr, v, s) for v in views for s in (0, 1, 2)]))
+        torch.save(dict(rec=rec, n_coll=n_coll), os.path.join(out_dir, f'mb{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_view_batched_step_host_logic_two_ranks():
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_mb_worker, args=(world, os.path.join(d, 'store'), d), nprocs=world, join=True)
+        r = [torch.load(os.path.join(d, f'mb{k}.pt')) for k in range(world)]
+    assert r[0]['n_coll'] == r[1]['n_coll'] == 3                                   # one collective per step
+    # the single-rank result of the same three steps
+    net = _TinyField()
+    opt = FlatAdam(net, lr=5e-4)
+    for step in range(3):
+        a, b = r[0]['rec'][step], r[1]['rec'][step]
+        assert a['views'] == b['views'] and len(set(a['views'])) == 4             # same permutation stream on every rank
+        assert sorted(a['mine'] + b['mine']) == sorted(a['views']) and not set(a['mine']) & set(b['mine'])
+        assert a['seeds'] == b['seeds'] and len(set(a['seeds'])) == len(a['seeds'])   # per-(iteration, view, stream) seeds, independent of the rank
+        assert a['owner'] != b['owner']                                             # exactly one rank computes the photometric term
+        assert torch.equal(a['summed'], b['summed'])
+        assert torch.allclose(a['summed'], a['local'] + b['local'], rtol=0, atol=0)
+    from sparsefusion_b200.distillation import KeyedNoise
+    n1 = KeyedNoise([5, 9], 'cpu', chunk=4)
+    n2 = KeyedNoise([9], 'cpu', chunk=4)
+    like2, like1 = torch.empty(2, 3, 2, 2), torch.empty(1, 3, 2, 2)
+    for _ in range(6):                                                              # crosses a chunk refill
+        assert torch.equal(n1(like2)[1], n2(like1)[0])                              # a view's noise does not depend on the batch it shares
