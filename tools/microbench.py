@@ -61,7 +61,7 @@ def unet_bench(out):
     for mode in (('tf32x3',) if 'x3only' in sys.argv else ('tf32x3', 'tf32')):
         ops.set_precision(mode)
         unet.prepare()
-        for nb in ((1, 8, 16) if 'nb16' in sys.argv else (1, 8)):
+        for nb in ((16, 32) if 'nb32' in sys.argv else (1, 8, 16) if 'nb16' in sys.argv else (1, 8)):
             x, cond, t = torch.randn(nb, 4, 32, 32, device='cuda'), torch.randn(nb, 256, 32, 32, device='cuda'), torch.full((nb,), 0.3, device='cuda')
             eager = timeit(lambda: unet.forward(x, t, cond_images=cond), iters=5, warmup=2, flush=False)
             runner = UnetGraph(unet)
@@ -95,7 +95,11 @@ def unet_trace(out):
     ops.set_precision('tf32x3')
     unet.parallel_res_conv = 'parallel' in sys.argv      # per-kernel attribution needs a single dependency chain
     unet.prepare()
-    x, cond, t = torch.randn(1, 4, 32, 32, device='cuda'), torch.randn(1, 256, 32, 32, device='cuda'), torch.full((1,), 0.3, device='cuda')
+    hw = 32
+    for a in sys.argv:
+        if a.startswith('hw='):
+            hw = int(a[3:])
+    x, cond, t = torch.randn(1, 4, hw, hw, device='cuda'), torch.randn(1, 256, hw, hw, device='cuda'), torch.full((1,), 0.3, device='cuda')
     runner = UnetGraph(unet)
     for _ in range(3):
         runner(x, t, cond)
