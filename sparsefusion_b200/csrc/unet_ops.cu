@@ -627,6 +627,83 @@ __global__ void __launch_bounds__(256) mq_attention_smem_kernel(const float* __r
         }
 }
 
+// Many keys (128 x 128 latents: 256 tokens + null + context at the deepest stage).  Same staging, but a LANE owns a key while scoring (rows
+// padded by four floats so the quarter-warps' float4 reads fall on 32 distinct banks), one warp maximum / sum per query instead of one shuffle
+// tree per key, and a warp walks `qpw` queries so that the 132 KB of keys and values is staged once per 8 qpw queries.
+__global__ void __launch_bounds__(256) mq_attention_keys_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                const float* __restrict__ null_kv, const float* __restrict__ ckv,
+                                                                float* __restrict__ out, int n, int heads, int dh, int nc, float scale, int round,
+                                                                int qpw) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm[];
+    const int nk = nc + 1 + n, nkp = (nk + 31) & ~31;
+    const int row = 2 * dh, rs = row + 4;
+    float* kvs = sm;                              // [nk][rs]
+    float* scs = sm + (size_t)nk * rs;            // [8][nkp]
+    float* qs = scs + 8 * nkp;                    // [8][dh]
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row4 = row >> 2;
+    for (int i = threadIdx.x; i < nk * row4; i += 256) {
+        const int j = i / row4, e4 = i - j * row4;
+        const float* src;
+        if (j < nc) src = ckv + ((int64_t)(b * nc + j)) * row;
+        else if (j == nc) src = null_kv;
+        else src = kv + ((int64_t)(b * n + (j - nc - 1))) * row;
+        *reinterpret_cast<float4*>(kvs + (size_t)j * rs + e4 * 4) = __ldg(reinterpret_cast<const float4*>(src) + e4);
+    }
+    __syncthreads();
+    float* sc = scs + warp * nkp;
+    float* qw = qs + warp * dh;
+    const int dh4 = dh >> 2;
+    for (int t = 0; t < qpw; ++t) {
+        const int qi = (blockIdx.x * 8 + warp) * qpw + t;     // query index over (head, token)
+        if (qi >= heads * n) break;
+        const int i = qi % n, h = qi / n;
+        const float* qr = q + ((int64_t)(b * n + i) * heads + h) * dh;
+        for (int e = lane; e < dh; e += 32) qw[e] = qr[e] * scale;
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < nk; j += 32) {
+            const float4* kr = reinterpret_cast<const float4*>(kvs + (size_t)j * rs);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll 4
+            for (int e4 = 0; e4 < dh4; ++e4) {
+                const float4 k4 = kr[e4];
+                const float4 q4 = reinterpret_cast<const float4*>(qw)[e4];
+                d0 += k4.x * q4.x + k4.y * q4.y;
+                d1 += k4.z * q4.z + k4.w * q4.w;
+            }
+            const float d = d0 + d1;
+            sc[j] = d;
+            mx = fmaxf(mx, d);
+        }
+        mx = warp_max(mx);
+        float den = 0.f;
+        for (int j = lane; j < nk; j += 32) { const float e = __expf(sc[j] - mx); sc[j] = e; den += e; }
+        den = warp_sum(den);
+        __syncwarp();
+        const float inv = 1.f / den;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int j = 0; j < nk; ++j) {
+            const float pj = sc[j];
+            const float* vr = kvs + (size_t)j * rs + dh;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (lane + 32 * u < dh) acc[u] += pj * vr[lane + 32 * u];
+        }
+        float* orow = out + ((int64_t)(b * n + i) * heads + h) * dh;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane + 32 * u < dh) {
+                const float v = acc[u] * inv;
+                orow[lane + 32 * u] = round ? tc::round_tf32(v) : v;
+            }
+        __syncwarp();
+    }
+}
+
 // Cross attention (imagen_pytorch.py:764-805): q [B,n,heads*dh]; kvc [B,nc,2*heads*dh] = (k | v) per context token, per-head slices;
 // null_kv [2,dh] shared by heads; keys: null, context.  One warp per (b, head, query).
 __global__ void cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const float* __restrict__ null_kv,
@@ -734,6 +811,80 @@ __global__ void __launch_bounds__(256) gca_pool_kernel(const float* __restrict__
     }
 }
 
+// Large images (128 x 128 latents: 16 384 pixels against 8 channel tiles of work): a thread-block CLUSTER of Z CTAs shares one (image, channel
+// tile); CTA z soft-maxes and pools its own slab of pixels (local maximum m_z, local sum s_z, local weighted sums a_z[16]) and rank 0 merges
+// the Z triples through distributed shared memory:  M = max m_z,  pooled = sum_z a_z e^(m_z - M) / sum_z s_z e^(m_z - M).
+__global__ void __launch_bounds__(256) gca_pool_split_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ logits,
+                                                            float* __restrict__ pooled, int HW, int C) {
+    pdl_sync();
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ float gca_sm[];
+    const unsigned Z = cl.num_blocks(), rank = cl.block_rank();
+    const int p0 = (int)(((int64_t)HW * rank) / Z), p1 = (int)(((int64_t)HW * (rank + 1)) / Z), np = p1 - p0;
+    float* wts = gca_sm;                       // [np]
+    float* part = gca_sm + ((np + 3) & ~3);    // [64][16]
+    __shared__ float red[8];
+    __shared__ __align__(16) float merged[2 + kGcaCols];     // m_z, s_z, a_z[16]: read by rank 0 through DSMEM
+    const int n = blockIdx.y, c0 = (int)(blockIdx.x / Z) * kGcaCols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* lg = logits + (int64_t)n * HW + p0;
+    float mx = -INFINITY;
+    for (int p = threadIdx.x; p < np; p += 256) { const float v = lg[p]; wts[p] = v; mx = fmaxf(mx, v); }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sm = 0.f;
+    for (int p = threadIdx.x; p < np; p += 256) { const float e = __expf(wts[p] - mx); wts[p] = e; sm += e; }
+    sm = warp_sum(sm);
+    if (lane == 0) red[warp] = sm;
+    __syncthreads();
+    const int pg = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const int c = c0 + q * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const float* xb = x + ((int64_t)n * HW + p0) * ldx + c;
+#pragma unroll 4
+        for (int p = pg; p < np; p += 64) {
+            const float w = wts[p];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)p * ldx));
+            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+    }
+    reinterpret_cast<float4*>(part)[pg * 4 + q] = acc;
+    __syncthreads();
+    if (threadIdx.x < kGcaCols) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int g = 0; g < 64; ++g) t += part[g * kGcaCols + threadIdx.x];
+        merged[2 + threadIdx.x] = t;
+    }
+    if (threadIdx.x == 32) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        merged[0] = mx;
+        merged[1] = tot;
+    }
+    cl.sync();
+    if (rank == 0 && threadIdx.x < kGcaCols && c0 + threadIdx.x < C) {
+        float M = -INFINITY;
+        for (unsigned z = 0; z < Z; ++z) M = fmaxf(M, cl.map_shared_rank(merged, z)[0]);
+        float S = 0.f, A = 0.f;
+        for (unsigned z = 0; z < Z; ++z) {
+            const float* mz = cl.map_shared_rank(merged, z);
+            const float f = __expf(mz[0] - M);
+            S += mz[1] * f;
+            A += mz[2 + threadIdx.x] * f;
+        }
+        pooled[(int64_t)n * C + c0 + threadIdx.x] = A / S;
+    }
+    cl.sync();      // no CTA leaves while rank 0 may still read its shared memory
+}
+
 // out = h * gate[n][c] + res      (ResnetBlock tail, imagen_pytorch.py:727-729); gate may be null (== 1)
 __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v, const float* __restrict__ gate, const float4* __restrict__ res,
                                      int64_t ldr_v, float4* __restrict__ out, int64_t ldo_v, int HW, int Cv, int64_t total) {
@@ -753,8 +904,9 @@ __global__ void gate_residual_kernel(const float4* __restrict__ h, int64_t ldh_v
 }
 
 // GlobalContext tail fused: gate[n][c] = sigmoid(b2[c] + W2[c][:] . hid[n][:]) (Conv2d(hidden, dim_out, 1) + Sigmoid, imagen_pytorch.py:929-933)
-// and out = h * gate + res (ResnetBlock tail, :727-729) in one launch.  grid (C / 8, NB): a CTA owns 8 channels of one image -- each warp
-// evaluates one gate channel (a 2 KB weight row), then all threads stream the CTA's 32-byte channel slab of every pixel.
+// and out = h * gate + res (ResnetBlock tail, :727-729) in one launch.  grid (C / 8, NB, Z): a CTA owns 8 channels of one image -- each warp
+// evaluates one gate channel (a 2 KB weight row), then all threads stream the CTA's 32-byte channel slab of the pixels p = 128 z + .., stride
+// 128 Z.  Z > 1 (large images: 16 384 pixels at 128 x 128 latents) recomputes the eight gates per CTA -- L2 hits -- to put every SM to work.
 __global__ void __launch_bounds__(256) gate_mlp_residual_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ hid,
                                                                const float* __restrict__ W2, const float* __restrict__ b2, int Hd,
                                                                const float* __restrict__ res, int64_t ldr, float* __restrict__ out, int64_t ldo, int HW,
@@ -790,8 +942,9 @@ __global__ void __launch_bounds__(256) gate_mlp_residual_kernel(const float* __r
     const float* hb = h + (int64_t)n * HW * ldh + c;
     const float* rb = res + (int64_t)n * HW * ldr + c;
     float* ob = out + (int64_t)n * HW * ldo + c;
+    const int pstep = 128 * (int)gridDim.z;
 #pragma unroll 4
-    for (int p = pg; p < HW; p += 128) {
+    for (int p = pg + 128 * (int)blockIdx.z; p < HW; p += pstep) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(hb + (int64_t)p * ldh));
         const float4 r = __ldg(reinterpret_cast<const float4*>(rb + (int64_t)p * ldr));
         *reinterpret_cast<float4*>(ob + (int64_t)p * ldo) = make_float4(v.x * g.x + r.x, v.y * g.y + r.y, v.z * g.z + r.z, v.w * g.w + r.w);
@@ -918,14 +1071,13 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
         while (k > 1 && (int)k > HW) k >>= 1;
         const int64_t per_cta = (int64_t)((HW + (int)k - 1) / (int)k) * (Cg / 4);
         const int items = (int)((per_cta + 255) / 256);
-        if (items <= 32) {
+        if (items <= 16) {     // beyond that (128 x 128 latents) 64 CTAs cannot pull the bandwidth: 47.7 us against 25 us for the two row-coalesced launches
             const dim3 grid(G * k, NB);
             const int rnd = (int)(precision_mode() == 0);
             cudaError_t e;
             if (items <= 4) e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<4>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
             else if (items <= 8) e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<8>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
-            else if (items <= 16) e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<16>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
-            else e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<32>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
+            else e = SFB_LAUNCH_CLUSTER(gn_cluster_kernel<16>, grid, 256, 0, st, k, x, ldx, HW, C, G, eps, gamma, beta, film, film_ld, y, ldy, act_silu, rnd);
             (void)e;
             return check_launch("groupnorm_nhwc(cluster)");
         }
@@ -991,6 +1143,18 @@ int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, cons
                      float scale, void* stream) {
     SFB_REQUIRE(q && kv && null_kv && out && (nc == 0 || ckv), "mq_attention: null pointer");
     const int nk = nc + 1 + n;
+    if (nk > 64 && dh % 4 == 0 && dh <= 128) {
+        const size_t smk = ((size_t)nk * (2 * dh + 4) + (size_t)8 * ((nk + 31) & ~31) + (size_t)8 * dh) * 4;
+        if (smk <= 200 * 1024) {
+            // queries per warp: about one CTA per SM over the batch
+            int qpw = ceil_div(heads * n * B, 8 * sm_count());
+            if (qpw < 1) qpw = 1;
+            SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(mq_attention_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+            SFB_LAUNCH(mq_attention_keys_kernel, dim3(ceil_div(heads * n, 8 * qpw), B), 256, smk, as_stream(stream), q, kv, null_kv, ckv, out, n, heads, dh, nc,
+                       scale, (int)(precision_mode() == 0), qpw);
+            return check_launch("mq_attention(keys)");
+        }
+    }
     {
         const size_t sm2 = ((size_t)nk * 2 * dh + (size_t)8 * nk) * 4;
         if (dh % 4 == 0 && dh <= 128 && sm2 <= 160 * 1024) {
@@ -1023,6 +1187,15 @@ int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float
     const int64_t npix = (int64_t)NB * HW;
     SFB_LAUNCH(gca_logits_kernel, (unsigned)ceil_div(npix, (int64_t)8), 256, 0, st, x, ldx, wk, bk, logits_ws, npix, C);
     if (int rc = check_launch("gca_pool(logits)")) return rc;
+    if (HW >= 4096) {          // pixel-split clusters: 8 CTAs per (image, 16-channel tile)
+        const unsigned Z = 8;
+        const size_t sms = ((size_t)(((HW + (int)Z - 1) / (int)Z + 4) & ~3) + 64 * kGcaCols) * 4;
+        SFB_REQUIRE(sms <= 200 * 1024, "gca_pool: image too large");
+        if (sms > 48 * 1024) SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(gca_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+        cudaError_t e = SFB_LAUNCH_CLUSTER(gca_pool_split_kernel, dim3(Z * ceil_div(C, kGcaCols), NB), 256, sms, st, Z, x, ldx, (const float*)logits_ws, pooled, HW, C);
+        (void)e;
+        return check_launch("gca_pool(pool, split)");
+    }
     const size_t sm = ((size_t)((HW + 3) & ~3) + 64 * kGcaCols) * 4;
     SFB_REQUIRE(sm <= 200 * 1024, "gca_pool: image too large for the single-pass pooling kernel (softmax weights of one image live in shared memory)");
     if (sm > 48 * 1024) SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(gca_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
@@ -1035,7 +1208,11 @@ int sfb_gate_mlp_residual_nhwc(const float* h, int64_t ldh, const float* hid, co
     SFB_REQUIRE(h && hid && w2 && b2 && res && out, "gate_mlp_residual: null pointer");
     SFB_REQUIRE(C % 4 == 0 && ldh % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && Hd > 0, "gate_mlp_residual: channel counts must be multiples of 4");
     if (NB == 0 || HW == 0) return SFB_OK;
-    SFB_LAUNCH(gate_mlp_residual_kernel, dim3(ceil_div(C, 8), NB), 256, 0, as_stream(stream), h, ldh, hid, w2, b2, Hd, res, ldr, out, ldo, HW, C);
+    // pixel split: about two CTAs per SM over the batch, at least four 128-pixel passes per CTA
+    int Z = (2 * sm_count()) / (ceil_div(C, 8) * NB);
+    if (Z > HW / 512) Z = HW / 512;
+    if (Z < 1) Z = 1;
+    SFB_LAUNCH(gate_mlp_residual_kernel, dim3(ceil_div(C, 8), NB, Z), 256, 0, as_stream(stream), h, ldh, hid, w2, b2, Hd, res, ldr, out, ldo, HW, C);
     return check_launch("gate_mlp_residual");
 }
 

@@ -48,7 +48,7 @@ def gn_path(request):
 
 @pytest.mark.parametrize('shape', [(2, 16, 16, 64, 8), (1, 32, 32, 256, 8), (3, 4, 4, 1024, 8), (1, 32, 32, 512, 8), (1, 4, 4, 2048, 8),
                                    (2, 5, 7, 96, 8), (1, 64, 64, 512, 8), (2, 16, 16, 32, 32), (1, 8, 8, 64, 32), (1, 8, 8, 24, 4), (1, 64, 64, 128, 32), (2, 128, 128, 256, 32), (1, 16, 16, 512, 8), (1, 8, 8, 1024, 8), (1, 8, 8, 2048, 8), (1, 4, 4, 1024, 8),
-                                   (1, 16, 16, 768, 8), (1, 3, 5, 256, 8), (1, 32, 32, 128, 32)])
+                                   (1, 16, 16, 768, 8), (1, 3, 5, 256, 8), (1, 32, 32, 128, 32), (1, 128, 128, 128, 8), (1, 128, 128, 256, 8)])
 @pytest.mark.parametrize('film', [False, True])
 def test_groupnorm_film_silu(shape, film, gn_path):
     from sparsefusion_b200 import ops
@@ -103,7 +103,7 @@ def test_time_fourier():
 
 
 @pytest.mark.parametrize('nc', [0, 2])
-@pytest.mark.parametrize('n,heads,dh', [(16, 8, 64), (64, 4, 32), (37, 3, 128), (400, 2, 64)])   # the last one exceeds the smem-staged kernel
+@pytest.mark.parametrize('n,heads,dh', [(16, 8, 64), (64, 4, 32), (37, 3, 128), (256, 8, 64), (100, 2, 96), (400, 2, 64)])   # > 64 keys: lane-per-key kernel; the last one exceeds shared memory
 def test_mq_attention(nc, n, heads, dh):
     from sparsefusion_b200 import ops
     b = 2
@@ -143,7 +143,8 @@ def test_cross_attention():
     _close(out, ref, TF32, 2e-5)
 
 
-@pytest.mark.parametrize('shape', [(2, 16, 16, 256), (1, 32, 32, 256), (1, 4, 4, 1024), (3, 8, 8, 1024), (2, 3, 1, 64), (1, 16, 16, 512), (1, 8, 8, 96)])
+@pytest.mark.parametrize('shape', [(2, 16, 16, 256), (1, 32, 32, 256), (1, 4, 4, 1024), (3, 8, 8, 1024), (2, 3, 1, 64), (1, 16, 16, 512), (1, 8, 8, 96),
+                                   (1, 128, 128, 128), (2, 64, 64, 256), (1, 70, 60, 96)])   # >= 4096 pixels: pixel-split cluster pooling
 def test_gca_pool_and_gate_residual(shape):
     from sparsefusion_b200 import ops
     nb, h, w, c = shape
@@ -160,7 +161,7 @@ def test_gca_pool_and_gate_residual(shape):
     _close(ops.gate_residual(x, None, res), x + res, 1e-6, 1e-6)
 
 
-@pytest.mark.parametrize('shape', [(1, 32, 32, 256), (2, 4, 4, 1024), (3, 5, 3, 36)])
+@pytest.mark.parametrize('shape', [(1, 32, 32, 256), (2, 4, 4, 1024), (3, 5, 3, 36), (1, 128, 128, 128), (1, 50, 41, 64)])
 def test_gate_mlp_residual(shape):
     from sparsefusion_b200 import ops
     nb, h, w, c = shape
