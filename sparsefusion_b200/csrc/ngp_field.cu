@@ -577,7 +577,13 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ D, const fl
 #pragma unroll
         for (int jr = 0; jr < 4; ++jr)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[jr][r] += (d[jr].x * h[r].x + d[jr].y * h[r].y) + (d[jr].z * h[r].z + d[jr].w * h[r].w);
+            for (int r = 0; r < NR; ++r) {      // four chained FFMAs (a pairwise tree costs 2 FMUL + 2 FFMA + 2 FADD: a third more issue slots)
+                float t = acc[jr][r];
+                t = fmaf(d[jr].x, h[r].x, t);
+                t = fmaf(d[jr].y, h[r].y, t);
+                t = fmaf(d[jr].z, h[r].z, t);
+                acc[jr][r] = fmaf(d[jr].w, h[r].w, t);
+            }
     }
 }
 
@@ -645,25 +651,29 @@ __global__ void __launch_bounds__(kPT) field_forward_v2_kernel(PointSource ps, u
     }
 }
 
-// ---- 256-thread variants of the tile primitives for the backward (two threads per point: 8 warps on the one CTA an SM holds) --------------------
-constexpr int kBT = 256;          // threads of the backward CTA; the tile is still kPT = 128 points
+// ---- backward: 64-point tiles, 128 threads (two per point), three activation buffers -> 94 KB of shared memory, TWO CTAs per SM, so that one
+// CTA's gather / scatter phases (latency bound) overlap the other's FFMA phases.  (Round-2 history: 128-point tiles with one CTA per SM ran every
+// phase of the tile back to back on 4 or 8 warps: 4.57 / 4.36 ms for the 2.1 M points of a render.)
+constexpr int kPB = 64;           // points per backward tile
+constexpr int kLdB = kPB + 4;     // feature-major row stride (floats): 16-byte aligned rows, conflict-free float4 column reads
+constexpr int kBT = 128;          // threads of the backward CTA
 
-// Out[j][p] = epi(sum_k WT[k][j] * A[k][p]): thread (tp = t & 15, tj = t >> 4) owns outputs 4 tj .. 4 tj + 3 of points {4 tp ..} u {64 + 4 tp ..}
+// Out[j][p] = epi(sum_k WT[k][j] * A[k][p]): thread (tp = t & 7, tj = t >> 3) owns outputs 4 tj .. 4 tj + 3 of points {4 tp ..} u {32 + 4 tp ..}.
+// EPI 0: + bias, ReLU.  EPI 1: masked by the sign of what Out held before (the forward activation it overwrites) -- in place.
 template <int K, int EPI>
-__device__ __forceinline__ void dense_tile64_t256(const float* __restrict__ WT, const float* __restrict__ bias, const float* __restrict__ A,
-                                                  float* __restrict__ Out, const float* __restrict__ G) {
-    const int tp = threadIdx.x & 15, tj = threadIdx.x >> 4;
+__device__ __forceinline__ void dense64_p64(const float* __restrict__ WT, const float* __restrict__ bias, const float* __restrict__ A, float* Out) {
+    const int tp = threadIdx.x & 7, tj = threadIdx.x >> 3;
     float acc[4][8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float b = bias ? bias[tj * 4 + j] : 0.f;
+        const float b = EPI == 0 ? bias[tj * 4 + j] : 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] = b;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLd + tp * 4);
-        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLd + 64 + tp * 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLdB + tp * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLdB + 32 + tp * 4);
         const float4 w0 = *reinterpret_cast<const float4*>(WT + k * kHid + tj * 4);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float w[4] = {w0.x, w0.y, w0.z, w0.w};
@@ -674,35 +684,35 @@ __device__ __forceinline__ void dense_tile64_t256(const float* __restrict__ WT, 
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int row = (tj * 4 + j) * kLd;
+        float* row = Out + (tj * 4 + j) * kLdB;
         float o[8];
         if (EPI == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = fmaxf(acc[j][i], 0.f);
         } else {
-            const float4 g0 = *reinterpret_cast<const float4*>(G + row + tp * 4);
-            const float4 g1 = *reinterpret_cast<const float4*>(G + row + 64 + tp * 4);
+            const float4 g0 = *reinterpret_cast<const float4*>(row + tp * 4);
+            const float4 g1 = *reinterpret_cast<const float4*>(row + 32 + tp * 4);
             const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = gg[i] > 0.f ? acc[j][i] : 0.f;
         }
-        *reinterpret_cast<float4*>(Out + row + tp * 4) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(Out + row + 64 + tp * 4) = make_float4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<float4*>(row + tp * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(row + 32 + tp * 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
 
-// D0[k][p] = sum_j W0[j][k] * D1[j][p] (32 x 128, reduction 64): thread (tp = t & 15, tk = t >> 4) owns outputs 2 tk, 2 tk + 1
-__device__ __forceinline__ void dense_tile32_t256(const float* __restrict__ W0, const float* __restrict__ A, float* __restrict__ Out) {
-    const int tp = threadIdx.x & 15, tk = threadIdx.x >> 4;
+// D0[k][p] = sum_j W0[j][k] * D1[j][p] (32 x 64, reduction 64): thread (tp = t & 7, tk = t >> 3) owns outputs 2 tk, 2 tk + 1
+__device__ __forceinline__ void dense32_p64(const float* __restrict__ W0, const float* __restrict__ A, float* __restrict__ Out) {
+    const int tp = threadIdx.x & 7, tk = threadIdx.x >> 3;
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < kHid; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLd + tp * 4);
-        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLd + 64 + tp * 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(A + k * kLdB + tp * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + k * kLdB + 32 + tp * 4);
         const float2 w0 = *reinterpret_cast<const float2*>(W0 + k * kIn + tk * 2);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -710,33 +720,50 @@ __device__ __forceinline__ void dense_tile32_t256(const float* __restrict__ W0, 
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const int row = (tk * 2 + j) * kLd;
-        *reinterpret_cast<float4*>(Out + row + tp * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-        *reinterpret_cast<float4*>(Out + row + 64 + tp * 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        float* row = Out + (tk * 2 + j) * kLdB;
+        *reinterpret_cast<float4*>(row + tp * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        *reinterpret_cast<float4*>(row + 32 + tp * 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
     }
 }
 
-// acc[jr][r] += sum_p D[2 tj + jr][p] * H[tk + 8 r][p]: thread (tk = t & 7, tj = t >> 3 in 0..31) -- rows 2 tj, 2 tj + 1 of D, NR rows of H
+// acc[jr][r] += sum_p D[4 tj + jr][p] * H[tk + 8 r][p]: thread (tk = t & 7, tj = t >> 3 in 0..15)
 template <int NR>
-__device__ __forceinline__ void wgrad_tile_t256(const float* __restrict__ D, const float* __restrict__ H, float (&acc)[2][NR]) {
+__device__ __forceinline__ void wgrad_p64(const float* __restrict__ D, const float* __restrict__ H, float (&acc)[4][NR]) {
     const int tk = threadIdx.x & 7, tj = threadIdx.x >> 3;
 #pragma unroll 2
-    for (int p = 0; p < kPT; p += 4) {
-        float4 d[2], h[NR];
+    for (int p = 0; p < kPB; p += 4) {
+        float4 d[4], h[NR];
 #pragma unroll
-        for (int jr = 0; jr < 2; ++jr) d[jr] = *reinterpret_cast<const float4*>(D + (tj * 2 + jr) * kLd + p);
+        for (int jr = 0; jr < 4; ++jr) d[jr] = *reinterpret_cast<const float4*>(D + (tj * 4 + jr) * kLdB + p);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) h[r] = *reinterpret_cast<const float4*>(H + (tk + 8 * r) * kLd + p);
+        for (int r = 0; r < NR; ++r) h[r] = *reinterpret_cast<const float4*>(H + (tk + 8 * r) * kLdB + p);
 #pragma unroll
-        for (int jr = 0; jr < 2; ++jr)
+        for (int jr = 0; jr < 4; ++jr)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[jr][r] += (d[jr].x * h[r].x + d[jr].y * h[r].y) + (d[jr].z * h[r].z + d[jr].w * h[r].w);
+            for (int r = 0; r < NR; ++r) {      // four chained FFMAs (a pairwise tree costs 2 FMUL + 2 FFMA + 2 FADD: a third more issue slots)
+                float t = acc[jr][r];
+                t = fmaf(d[jr].x, h[r].x, t);
+                t = fmaf(d[jr].y, h[r].y, t);
+                t = fmaf(d[jr].z, h[r].z, t);
+                acc[jr][r] = fmaf(d[jr].w, h[r].w, t);
+            }
     }
 }
 
-// encode levels [l0, l0 + nl) of one point into column `col` of E
-__device__ __forceinline__ void encode_levels_tile(const float (&x)[3], bool valid, const float* __restrict__ table, const int32_t* __restrict__ offsets,
-                                                   const FieldGeom& g, float* __restrict__ E, int col, uint32_t l0, uint32_t nl) {
+// sum of one 64-float row
+__device__ __forceinline__ float row_sum_p64(const float* __restrict__ row) {
+    float t = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < kPB; q += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(row + q);
+        t += (v.x + v.y) + (v.z + v.w);
+    }
+    return t;
+}
+
+// encode levels [l0, l0 + nl) of one point into column `col` of E (row stride kLdB)
+__device__ __forceinline__ void encode_levels_p64(const float (&x)[3], bool valid, const float* __restrict__ table, const int32_t* __restrict__ offsets,
+                                                  const FieldGeom& g, float* __restrict__ E, int col, uint32_t l0, uint32_t nl) {
     float u[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(__fadd_rn(x[d], g.bound), 2 * g.bound);
@@ -768,11 +795,11 @@ __device__ __forceinline__ void encode_levels_tile(const float (&x)[3], bool val
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) E[(2 * level + q) * kLd + col] = a[q];
+        for (int q = 0; q < 4; ++q) E[(2 * level + q) * kLdB + col] = a[q];
     }
 }
 
-__global__ void __launch_bounds__(kBT, 1) field_backward_v2_kernel(PointSource ps, uint32_t B, const float* __restrict__ table, const int32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(kBT, 2) field_backward_v2_kernel(PointSource ps, uint32_t B, const float* __restrict__ table, const int32_t* __restrict__ offsets,
                                                                   FieldGeom g, const float* __restrict__ W0, const float* __restrict__ b0,
                                                                   const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                                                                   const float* __restrict__ b2, const float* __restrict__ g_sigma,
@@ -781,48 +808,48 @@ __global__ void __launch_bounds__(kBT, 1) field_backward_v2_kernel(PointSource p
                                                                   float* __restrict__ gW2, float* __restrict__ gb2) {
     extern __shared__ __align__(16) uint8_t smraw[];
     FieldSmemV2Bwd& s = *reinterpret_cast<FieldSmemV2Bwd*>(smraw);
-    float* bufA = reinterpret_cast<float*>(smraw + sizeof(FieldSmemV2Bwd));   // E rows 0..31 | D0 rows 32..63
-    float* bufB = bufA + kHid * kLd;                                          // H1
-    float* bufC = bufB + kHid * kLd;                                          // H2, then D1
-    float* bufD = bufC + kHid * kLd;                                          // D2
+    float* bufA = reinterpret_cast<float*>(smraw + sizeof(FieldSmemV2Bwd));   // E (32 rows)
+    float* bufB = bufA + kIn * kLdB;                                          // H1, then D1 in place
+    float* bufC = bufB + kHid * kLdB;                                         // H2, then D2 in place, then D0 (rows 0..31)
     load_weights_v2(s.f, W0, b0, W1, b1, W2, b2);
     for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x) s.W1[i] = W1[i];
     for (int i = threadIdx.x; i < kHid * kIn; i += blockDim.x) s.W0[i] = W0[i];
     __syncthreads();
     const int tid = threadIdx.x;
-    const int pt = tid & (kPT - 1), half = tid >> 7;       // two threads per point: levels / hidden units [8 half, 8 half + 8) resp. [32 half, 32 half + 32)
+    const int pt = tid & (kPB - 1), half = tid >> 6;       // two threads per point: levels [8 half, 8 half + 8), hidden units [32 half, 32 half + 32)
     // per-thread shares of the weight gradients, kept in registers over all tiles of this CTA
-    float aW1[2][8], aW0[2][4];
+    float aW1[4][8], aW0[4][4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) aW1[a][r] = 0.f;
 #pragma unroll
         for (int r = 0; r < 4; ++r) aW0[a][r] = 0.f;
     }
-    float aW2 = 0.f;                // dW2[c][k]: k = tid & 63, c = tid >> 6
-    float ab = 0.f;                 // tid < 64: db1[tid]; 64 <= tid < 128: db0[tid - 64]; 128 <= tid < 132: db2[tid - 128]
-    const uint32_t tiles = (B + kPT - 1) / kPT;
+    float aW2[2] = {0.f, 0.f};      // dW2[c][k]: k = tid & 63, c = (tid >> 6) + 2 i
+    float ab1 = 0.f;                // tid < 64: db1[tid]; tid >= 64: db0[tid - 64]
+    float ab2 = 0.f;                // tid < 4: db2[tid]
+    const uint32_t tiles = (B + kPB - 1) / kPB;
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint32_t p = tile * kPT + pt;
+        const uint32_t p = tile * kPB + pt;
         const bool valid = p < B;
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) fetch_point(ps, p, x);
         // ---- forward recompute: E -> H1 -> H2
-        encode_levels_tile(x, valid, table, offsets, g, bufA, pt, half * 8, 8);
+        encode_levels_p64(x, valid, table, offsets, g, bufA, pt, half * 8, 8);
         __syncthreads();
-        dense_tile64_t256<kIn, 0>(s.f.WT0, s.f.b0, bufA, bufB, nullptr);
+        dense64_p64<kIn, 0>(s.f.WT0, s.f.b0, bufA, bufB);
         __syncthreads();
-        dense_tile64_t256<kHid, 0>(s.f.WT1, s.f.b1, bufB, bufC, nullptr);
+        dense64_p64<kHid, 0>(s.f.WT1, s.f.b1, bufB, bufC);
         __syncthreads();
-        // ---- output layer and its gradient (one thread per point), then D2 = relu'(H2) (W2^T d3) (two threads per point)
+        // ---- output layer and its gradient d3 (one thread per point)
         if (half == 0) {
             float d3[4] = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 float o[4] = {s.f.b2[0], s.f.b2[1], s.f.b2[2], s.f.b2[3]};
 #pragma unroll 8
                 for (int k = 0; k < kHid; ++k) {
-                    const float hk = bufC[k * kLd + pt];
+                    const float hk = bufC[k * kLdB + pt];
                     const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
                     o[0] += w.x * hk; o[1] += w.y * hk; o[2] += w.z * hk; o[3] += w.w * hk;
                 }
@@ -835,58 +862,48 @@ __global__ void __launch_bounds__(kBT, 1) field_backward_v2_kernel(PointSource p
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) s.d3[c * kLd + pt] = d3[c];
+            for (int c = 0; c < 4; ++c) s.d3[c * kLdB + pt] = d3[c];
         }
         __syncthreads();
+        // ---- dW2 += d3 H2^T, db2
         {
-            const float d0 = s.d3[pt], d1 = s.d3[kLd + pt], d2 = s.d3[2 * kLd + pt], d3v = s.d3[3 * kLd + pt];
+            const int k = tid & 63, c = tid >> 6;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < kPB; q += 4) {
+                const float4 h = *reinterpret_cast<const float4*>(bufC + k * kLdB + q);
+                const float4 da = *reinterpret_cast<const float4*>(s.d3 + c * kLdB + q);
+                const float4 db = *reinterpret_cast<const float4*>(s.d3 + (c + 2) * kLdB + q);
+                s0 = fmaf(da.w, h.w, fmaf(da.z, h.z, fmaf(da.y, h.y, fmaf(da.x, h.x, s0))));
+                s1 = fmaf(db.w, h.w, fmaf(db.z, h.z, fmaf(db.y, h.y, fmaf(db.x, h.x, s1))));
+            }
+            aW2[0] += s0;
+            aW2[1] += s1;
+            if (tid < 4) ab2 += row_sum_p64(s.d3 + tid * kLdB);
+        }
+        __syncthreads();     // every reader of H2 is done before D2 overwrites it
+        // ---- D2 = relu'(H2) (W2^T d3), in place (two threads per point)
+        {
+            const float d0 = s.d3[pt], d1 = s.d3[kLdB + pt], d2 = s.d3[2 * kLdB + pt], d3v = s.d3[3 * kLdB + pt];
 #pragma unroll 8
             for (int k = half * 32; k < half * 32 + 32; ++k) {
                 const float4 w = *reinterpret_cast<const float4*>(s.f.WT2 + k * kOut);
                 const float v = w.x * d0 + w.y * d1 + w.z * d2 + w.w * d3v;
-                bufD[k * kLd + pt] = bufC[k * kLd + pt] > 0.f ? v : 0.f;
+                bufC[k * kLdB + pt] = bufC[k * kLdB + pt] > 0.f ? v : 0.f;
             }
         }
         __syncthreads();
-        // ---- dW2 += d3 H2^T, db2, db1 (D2 row sums)
-        {
-            const int k = tid & 63, c = tid >> 6;
-            float s0 = 0.f;
-#pragma unroll 4
-            for (int q = 0; q < kPT; q += 4) {
-                const float4 h = *reinterpret_cast<const float4*>(bufC + k * kLd + q);
-                const float4 da = *reinterpret_cast<const float4*>(s.d3 + c * kLd + q);
-                s0 += (da.x * h.x + da.y * h.y) + (da.z * h.z + da.w * h.w);
-            }
-            aW2 += s0;
-            if (tid < 64 || (tid >= 128 && tid < 132)) {
-                const float* src = tid < 64 ? bufD + tid * kLd : s.d3 + (tid - 128) * kLd;
-                float t = 0.f;
-#pragma unroll 4
-                for (int q = 0; q < kPT; q += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(src + q);
-                    t += (v.x + v.y) + (v.z + v.w);
-                }
-                ab += t;
-            }
-        }
-        __syncthreads();     // every reader of H2 (bufC) is done before D1 overwrites it
-        // ---- D1 = relu'(H1) (W1^T D2) -> bufC ; dW1 += D2 H1^T
-        dense_tile64_t256<kHid, 1>(s.W1, nullptr, bufD, bufC, bufB);
-        wgrad_tile_t256<8>(bufD, bufB, aW1);
+        // ---- dW1 += D2 H1^T, db1
+        wgrad_p64<8>(bufC, bufB, aW1);
+        if (tid < 64) ab1 += row_sum_p64(bufC + tid * kLdB);
+        __syncthreads();     // every reader of H1 is done before D1 overwrites it
+        // ---- D1 = relu'(H1) (W1^T D2), in place over H1
+        dense64_p64<kHid, 1>(s.W1, nullptr, bufC, bufB);
         __syncthreads();
-        // ---- D0 = W0^T D1 -> bufA rows 32..63 ; dW0 += D1 E^T ; db0
-        dense_tile32_t256(s.W0, bufC, bufA + kIn * kLd);
-        wgrad_tile_t256<4>(bufC, bufA, aW0);
-        if (tid >= 64 && tid < 128) {
-            float t = 0.f;
-#pragma unroll 4
-            for (int q = 0; q < kPT; q += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(bufC + (tid - 64) * kLd + q);
-                t += (v.x + v.y) + (v.z + v.w);
-            }
-            ab += t;
-        }
+        // ---- D0 = W0^T D1 -> bufC rows 0..31 (D2 is dead) ; dW0 += D1 E^T ; db0
+        dense32_p64(s.W0, bufB, bufC);
+        wgrad_p64<4>(bufB, bufA, aW0);
+        if (tid >= 64) ab1 += row_sum_p64(bufB + (tid - 64) * kLdB);
         __syncthreads();
         // ---- scatter D0 into the embedding gradient (kernel_grid_backward, gridencoder.cu:226-313): two threads per point, two levels per batch
         if (valid) {
@@ -900,7 +917,7 @@ __global__ void __launch_bounds__(kBT, 1) field_backward_v2_kernel(PointSource p
                     locate_2levels(u, level, offsets, g, c);
                     float gq[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) gq[q] = bufA[(kIn + 2 * level + q) * kLd + pt];
+                    for (int q = 0; q < 4; ++q) gq[q] = bufC[(2 * level + q) * kLdB + pt];
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
                         const int i0 = 2 * m, i1 = i0 + 1;
@@ -920,22 +937,23 @@ __global__ void __launch_bounds__(kBT, 1) field_backward_v2_kernel(PointSource p
                 }
             }
         }
-        __syncthreads();     // bufA / bufB / bufC / bufD are rewritten by the next tile
+        __syncthreads();     // the buffers are rewritten by the next tile
     }
     // ---- one reduction per CTA
     {
         const int tk = tid & 7, tj = tid >> 3;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) atomicAdd(gW1 + (size_t)(tj * 2 + a) * kHid + tk + 8 * r, aW1[a][r]);
+            for (int r = 0; r < 8; ++r) atomicAdd(gW1 + (size_t)(tj * 4 + a) * kHid + tk + 8 * r, aW1[a][r]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) atomicAdd(gW0 + (size_t)(tj * 2 + a) * kIn + tk + 8 * r, aW0[a][r]);
+            for (int r = 0; r < 4; ++r) atomicAdd(gW0 + (size_t)(tj * 4 + a) * kIn + tk + 8 * r, aW0[a][r]);
         }
-        atomicAdd(gW2 + (size_t)(tid >> 6) * kHid + (tid & 63), aW2);
-        if (tid < 64) atomicAdd(gb1 + tid, ab);
-        else if (tid < 128) atomicAdd(gb0 + (tid - 64), ab);
-        else if (tid < 132) atomicAdd(gb2 + (tid - 128), ab);
+        atomicAdd(gW2 + (size_t)(tid >> 6) * kHid + (tid & 63), aW2[0]);
+        atomicAdd(gW2 + (size_t)((tid >> 6) + 2) * kHid + (tid & 63), aW2[1]);
+        if (tid < 64) atomicAdd(gb1 + tid, ab1);
+        else atomicAdd(gb0 + (tid - 64), ab1);
+        if (tid < 4) atomicAdd(gb2 + tid, ab2);
     }
 }
 
@@ -996,10 +1014,10 @@ int sfb_ngp_field_backward(const float* xyz, const float* rays_o, const float* r
     if (B == 0) return SFB_OK;
     if (field_v2_enabled()) {
         // tiled kernel: activations stay in shared memory, weight gradients accumulate in registers per CTA -- `tape` is not touched
-        const size_t smem2 = sizeof(FieldSmemV2Bwd) + (size_t)4 * kHid * kLd * 4;
+        const size_t smem2 = sizeof(FieldSmemV2Bwd) + (size_t)(kIn + 2 * kHid) * kLdB * 4;
         SFB_ONCE_PER_DEVICE(SFB_CUDA(cudaFuncSetAttribute(field_backward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)));
-        const uint32_t tiles = ceil_div(B, (uint32_t)kPT);
-        const uint32_t blocks2 = min(tiles, (uint32_t)sm_count());
+        const uint32_t tiles = ceil_div(B, (uint32_t)kPB);
+        const uint32_t blocks2 = min(tiles, (uint32_t)sm_count() * 2);
         field_backward_v2_kernel<<<blocks2, kBT, smem2, as_stream(stream)>>>(make_source(xyz, rays_o, rays_d, z, T, bound), B, embeddings, offsets,
                                                                             FieldGeom{S, H, bound}, W0, b0, W1, b1, W2, b2, grad_sigma, grad_rgb,
                                                                             grad_embeddings, gW0, gb0, gW1, gb1, gW2, gb2);
