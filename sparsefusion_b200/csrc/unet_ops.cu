@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) gn_stats_rows_kernel(const float* __restr
     for (int pass = 0; pass < passes; ++pass) {
         const float* base = x + (int64_t)n * HW * ldx + (pass * 256 + tc) * 4;
         double s = 0.0, ss = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int p = p0 + tr; p < p1; p += rpi) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * ldx));
             s += (double)(v.x + v.y + v.z + v.w);
@@ -398,6 +398,93 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
             for (int k = 0; k < 4; ++k) o[k] = tc::round_tf32(o[k]);
         }
         *reinterpret_cast<float4*>(yn + pix * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Same contract for C/4 a divisor of 256 (every layer up to 1 024 channels): a thread keeps ONE float4 column, so its group statistics, affine and
+// FiLM coefficients are loaded once and the loop is load -> 3 FP ops per element -> store with no index division (the generic kernel above re-reads
+// five coefficient vectors and divides a 64-bit index per element: 31 us for the 33.5 MB tensors of the VAE decoder's 256 x 256 stage).
+__global__ void __launch_bounds__(256, 3) gn_apply_cols_kernel(const float* __restrict__ x, int64_t ldx, const double2* __restrict__ partial, int S, float eps,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ film, int64_t ldf, float* __restrict__ y, int64_t ldy, int HW, int C,
+                                                           int G, int act, int round) {
+    pdl_sync();
+    __shared__ float2 st_sh[kGnMaxGroups];
+    const int n = blockIdx.y;
+    const int Cg = C / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C4 = C >> 2, rpi = 256 / C4;
+    const int tc = threadIdx.x % C4, tr = threadIdx.x / C4;
+    const int c = tc * 4;
+    const float* xn = x + (int64_t)n * HW * ldx + c;
+    const int step = (int)gridDim.x * rpi;
+    const int pfirst = (int)blockIdx.x * rpi + tr;
+    // the thread's first eight rows are requested BEFORE the statistics are folded (independent of them): the fold's ~2 us hide under the loads
+    float4 v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int p = pfirst + i * step;
+        v8[i] = p < HW ? __ldg(reinterpret_cast<const float4*>(xn + (int64_t)p * ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int g = warp; g < G; g += 8) {
+        double ts = 0.0, tss = 0.0;
+        for (int k = lane; k < S; k += 32) {
+            const double2 pr = partial[((int64_t)n * G + g) * S + k];
+            ts += pr.x; tss += pr.y;
+        }
+        ts = warp_sum_d(ts);
+        tss = warp_sum_d(tss);
+        if (lane == 0) {
+            const double cnt = (double)HW * Cg;
+            const double mean = ts / cnt;
+            double var = tss / cnt - mean * mean;
+            if (var < 0) var = 0;
+            st_sh[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        }
+    }
+    __syncthreads();
+    float mu[4], a[4], b[4];       // y = (x - mu) a + b with the affine and the FiLM pair folded: a = rstd gamma (s + 1), b = beta (s + 1) + shift
+    {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float gv[4] = {ga.x, ga.y, ga.z, ga.w}, bv[4] = {be.x, be.y, be.z, be.w};
+        float fs[4] = {1.f, 1.f, 1.f, 1.f}, fh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (film) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + c));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(film + (int64_t)n * ldf + C + c));
+            fs[0] = sc.x + 1.f; fs[1] = sc.y + 1.f; fs[2] = sc.z + 1.f; fs[3] = sc.w + 1.f;
+            fh[0] = sh.x; fh[1] = sh.y; fh[2] = sh.z; fh[3] = sh.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 st = st_sh[(c + k) / Cg];
+            mu[k] = st.x;
+            a[k] = st.y * gv[k] * fs[k];
+            b[k] = bv[k] * fs[k] + fh[k];
+        }
+    }
+    float* yn = y + (int64_t)n * HW * ldy + c;
+    auto finish = [&](const float4& v, int p) {
+        float o[4] = {(v.x - mu[0]) * a[0] + b[0], (v.y - mu[1]) * a[1] + b[1], (v.z - mu[2]) * a[2] + b[2], (v.w - mu[3]) * a[3] + b[3]};
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
+        }
+        if (round) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = tc::round_tf32(o[k]);
+        }
+        *reinterpret_cast<float4*>(yn + (int64_t)p * ldy) = make_float4(o[0], o[1], o[2], o[3]);
+    };
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int p = pfirst + i * step;
+        if (p < HW) finish(v8[i], p);
+    }
+#pragma unroll 4
+    for (int p = pfirst + 8 * step; p < HW; p += step) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xn + (int64_t)p * ldx));
+        finish(v, p);
     }
 }
 
@@ -1063,7 +1150,9 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     const int C4 = C / 4, Cg = C / G;
     // ... for batches up to 4 images (<= 256 CTAs): it is a latency optimisation.  From batch 8 on the two-launch path's row-coalesced passes win
     // (batch-16 evaluation 5.87 ms against 6.38 ms)
-    if (gn_cluster_enabled() && (Cg % 16 == 0) && HW >= 1 && NB <= 4) {
+    // ... and for tensors of at most 1 Mi elements: 64 - 256 CTAs each reading 64-byte runs cannot pull the bandwidth a 64 x 64 x 512 VAE layer needs
+    // (35 us in the cluster kernel against ~25 us for the two row-coalesced launches)
+    if (gn_cluster_enabled() && (Cg % 16 == 0) && HW >= 1 && NB <= 4 && (int64_t)NB * HW * C <= (1 << 20)) {
         // one cluster of k CTAs per (image, group); a CTA holds ceil(HW/k) * Cg/4 float4 in registers.  Cg >= 16 keeps every pixel's share a
         // multiple of 64 contiguous bytes (full sectors); narrower groups (the VAE's 128-channel layers) stay on the row-coalesced two-launch path
         // always the widest portable cluster: narrower clusters (or a plain CTA per group) for the small stages measured slower (6.96 vs 5.98 us per launch)
@@ -1102,6 +1191,15 @@ int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G
     const int cap = (sm_count() * 8) / (NB < 1 ? 1 : NB);
     if (ab > cap) ab = cap < 1 ? 1 : cap;
     if (ab < 1) ab = 1;
+    if (C4 <= 256 && 256 % C4 == 0) {
+        const int rpi = 256 / C4;
+        int cb = (HW + rpi * 8 - 1) / (rpi * 8);          // ~8 rows per thread
+        const int cap3 = (cap * 3) / 8 < 1 ? 1 : (cap * 3) / 8;       // three resident CTAs per SM (84 registers: eight rows in flight per thread)
+        if (cb > cap3) cb = cap3;
+        SFB_LAUNCH(gn_apply_cols_kernel, dim3(cb, NB), 256, 0, st, x, ldx, (const double2*)partial, S, eps, gamma, beta, film, film_ld, y, ldy, HW, C, G,
+                   act_silu, (int)(precision_mode() == 0));
+        return check_launch("groupnorm_nhwc(apply, columns)");
+    }
     SFB_LAUNCH(gn_apply_kernel, dim3(ab, NB), 256, 0, st, x, ldx, (const double2*)partial, S, eps, gamma, beta, film, film_ld, y, ldy, HW, C, G, act_silu,
                (int)(precision_mode() == 0));
     return check_launch("groupnorm_nhwc(apply)");
