@@ -13,8 +13,10 @@ weights (torchvision VGG16 + the learned `lin` layers) that cannot be fetched.  
     d   = sum_k  mean_{h,w}  sum_c  w_k[c] * (n_k(x0) - n_k(x1))[c]^2         w_k >= 0, the 1x1 `lin` layers (bias-free; dropout is identity in eval)
 
 with SEEDED RANDOM weights of the right shapes (He-scaled convolutions so activations stay O(1) through 13 layers, non-negative lin weights).
-What the tests pin is therefore: the product kernels == this restatement (value and gradient w.r.t. x0) for identical weights; what they cannot
-pin is equality with the pretrained network's numbers.
+What the tests pin is therefore: the product kernels == this restatement (value and gradient w.r.t. x0) for identical weights, and the BACKBONE
+half of the restatement == torchvision 0.26's `vgg16().features` sliced where lpips slices it, for identical (random) weights
+(tests/test_oracle_lpips.py::test_backbone_taps_match_torchvision_vgg16); what they cannot pin is the `lin` heads / normalisation against the
+package's code, or equality with the pretrained network's numbers.
 """
 from __future__ import annotations
 

@@ -27,3 +27,34 @@ def test_metric_properties_and_gradient():
     eps = 1e-6
     fd = (lo.lpips(pd, x0.double() + eps * v, x1.double()) - lo.lpips(pd, x0.double() - eps * v, x1.double())).item() / (2 * eps)
     assert abs(fd - (a.grad * v).sum().item()) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_backbone_taps_match_torchvision_vgg16():
+    """The restated feature extractor against a real third-party implementation that IS in this image: torchvision's `vgg16().features`
+    (torchvision 0.26; random weights -- the pretrained ones cannot be fetched) sliced where lpips.pretrained_networks.vgg16 slices it
+    ([0:4], [4:9], [9:16], [16:23], [23:30] = relu1_2, relu2_2, relu3_3, relu4_3, relu5_3).  Pins layer order, padding, pooling and the tap
+    positions of the backbone half of the oracle; the `lin` heads and the normalisation stay a restatement of the published formula."""
+    tv = __import__('pytest').importorskip('torchvision')
+    p = lo.make_params(seed=3)
+    net = tv.models.vgg16(weights=None).features.eval()
+    convs = [m for m in net if isinstance(m, torch.nn.Conv2d)]
+    assert len(convs) == 13
+    with torch.no_grad():
+        for i, m in enumerate(convs):
+            m.weight.copy_(p[f'conv{i}.weight'])
+            m.bias.copy_(p[f'conv{i}.bias'])
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 48, 32, generator=g) * 2 - 1
+    shift = torch.tensor(lo.SHIFT).view(1, 3, 1, 1)
+    scale = torch.tensor(lo.SCALE).view(1, 3, 1, 1)
+    h = (x - shift) / scale
+    taps = []
+    with torch.no_grad():
+        for lo_i, hi_i in ((0, 4), (4, 9), (9, 16), (16, 23), (23, 30)):
+            for j in range(lo_i, hi_i):
+                h = net[j](h)
+            taps.append(h)
+    ours = lo.features(p, x)
+    for a, b in zip(ours, taps):
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
