@@ -194,8 +194,9 @@ int sfb_im2col4_nhwc(const float* x, int64_t ldx, float* out, int64_t ldo, int N
 int sfb_pixel_shuffle_silu_nhwc(const float* y, float* out, int NB, int H, int W, int Co, int64_t ldo, void* stream);
 /* Block: GroupNorm(G) -> optional FiLM (x*(scale+1)+shift, film rows [scale(C)|shift(C)] with row stride film_ld) -> optional SiLU (:654-661).
  * stats_ws: sfb_groupnorm_ws_floats(NB, G) floats of 16-byte aligned scratch (fp64 partial statistics per pixel slab).
- * Groups of >= 16 channels, batches of <= 4 images, per-CTA slab within the register file: ONE launch, one thread-block cluster of <= 8 CTAs per
- * (image, group), partial sums exchanged through distributed shared memory.  Otherwise two launches (row-coalesced statistics kernel + apply kernel).
+ * Groups of >= 16 channels, batches of <= 4 images, tensors of <= 1 Mi elements, per-CTA slab of <= 16 float4 per thread: ONE launch, one
+ * thread-block cluster of <= 8 CTAs per (image, group), partial sums exchanged through distributed shared memory.  Otherwise two launches
+ * (row-coalesced statistics kernel + apply kernel; the apply pass keeps one float4 column per thread when C/4 divides 256).
  * counters: unused since ABI 3 (round 1's single-launch variant met at a software grid barrier through these words); pass NULL.
  * Output is TF32-rounded in single-pass mode (it feeds the conv). */
 int sfb_groupnorm_nhwc(const float* x, int64_t ldx, int NB, int HW, int C, int G, const float* gamma, const float* beta, const float* film,
@@ -212,12 +213,15 @@ int sfb_linear_small(const float* x, int64_t ldx, const float* w, const float* b
                      int M, int K, int O, int pre, int post, int round_tf32, void* stream);
 /* LearnedSinusoidalPosEmb (:634-639): out [B, 2*half+1] */
 int sfb_time_fourier(const float* t, const float* w, float* out, int B, int half, void* stream);
-/* softmax(QK^T)V cores: multi-query self attention with null and context keys (:517-566) and cross attention (:770-805) */
+/* softmax(QK^T)V cores: multi-query self attention with null and context keys (:517-566) and cross attention (:770-805).
+ * sfb_mq_attention stages the keys / values of an image in shared memory (one warp per query up to 64 keys, a lane per key beyond: the 259 keys
+ * of the 128x128-latent configuration); key sets that do not fit 200 KB fall back to a global-memory kernel. */
 int sfb_mq_attention(const float* q, const float* kv, const float* null_kv, const float* ckv, float* out, int B, int n, int heads, int dh,
                      int nc, float scale, void* stream);
 int sfb_cross_attention(const float* q, const float* kvc, const float* null_kv, float* out, int B, int n, int heads, int dh, int nc,
                         float scale, void* stream);
-/* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW + 2*NB + 2 floats */
+/* GlobalContext (:936-940): pooled[n][c] = sum_p softmax_p(to_k(x))[p] x[n][p][c]; logits_ws NB*HW + 2*NB + 2 floats.
+ * From 4 096 pixels per image on, the pixels of a 16-channel slice are split over an 8-CTA cluster and merged through distributed shared memory. */
 int sfb_gca_pool(const float* x, int64_t ldx, int NB, int HW, int C, const float* wk, const float* bk, float* logits_ws, float* pooled,
                  void* stream);
 /* the same tail with GlobalContext's last layer folded in: gate[n][c] = sigmoid(b2[c] + w2[c][:] . hid[n][:]) (Conv2d(hidden, dim_out, 1) +
