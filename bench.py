@@ -44,6 +44,17 @@ WORKLOAD = ('sds_distillation_step: BASELINE configs[2] -- 2 input views, 64 cac
             '128x128 rays x (64+64) samples, PLMS(50), max_thres~U(0,0.99) seeded')
 
 
+def workload_config(world, mean_calls):
+    """`config` of the JSON line: the WORKLOAD only, built by one function so that both arms (ours and `--impl reference`) print the same object;
+    what describes an arm's engine (precision mode, VAE engine, host threads) goes into the sibling `engine` object."""
+    return {'workload': WORKLOAD,
+            'parallelism': f'dp{world} over target views, ' + ('no collective' if world == 1 else 'ONE 7.46 MB NGP-gradient all-reduce per step'),
+            'unet_evals_per_step_mean': None if mean_calls is None else round(float(mean_calls), 2),
+            'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
+            'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips '
+                     'package and its pretrained weights are un-vendored'}
+
+
 def max_thres_sequence(warmup, steps, seed=1234):
     """max_thres of every step (the reference draws U(0,1).clamp(0, .99) per step, distillation.py:303).  Warm-up steps get
     seeded uniform draws; the K timed steps get a seeded permutation of K equal strata of [0, .99], so that the mean PLMS
@@ -364,11 +375,8 @@ def run_gpu(args):
         out = {'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(value, 4), 'unit': 'steps/s', 'n_gpus': world,
                'steps': K, 'warmup': W, 'ms_per_step': round(ms / K, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f32 (UNet GEMMs: 3xTF32 error-compensated tensor-core passes, fp32 accumulate; NGP: fp32)', 'data': 'synthetic',
-               'config': {'workload': WORKLOAD, 'parallelism': f'dp{world} over target views, ' + ('no collective' if world == 1 else 'ONE 7.46 MB NGP-gradient all-reduce per step'),
-                          'unet_evals_per_step_mean': round(float(np.mean(n_calls)), 2) if n_calls else None,
-                          'l2': 'inputs larger than L2: each UNet evaluation streams 1.6 GB of fp32 weights (L2 = 126 MB)',
-                          'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored',
-                          'precision_mode': ops.get_precision()},
+               'config': workload_config(world, float(np.mean(n_calls)) if n_calls else None),
+               'engine': {'vae': 'sm_100a engine (tcgen05 3xTF32 convolutions / attention GEMMs, NHWC) -- SURVEY §8f row 1', 'precision_mode': ops.get_precision()},
                'clocks': clk, 'gpu_launches': int(launches),
                'e2e': None if e2e_val is None else {'value': round(e2e_val, 4), 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
                'roofline': roof, 'cpu_baseline': cpu,
@@ -623,8 +631,8 @@ def run_reference(args):
     out = {'impl': 'reference', 'metric': 'distillation-steps/sec (2-view, 256^2, 64 rendered views)', 'value': round(val, 6), 'unit': 'steps/s',
            'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': K, 'warmup': W, 'ms_per_step': round(step_s * 1e3, 1), 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': WORKLOAD, 'parallelism': f'host CPU, {port.threads} intra-op threads (fixed; the fastest count measured on the {os.cpu_count()}-thread host class)',
-                      'lpips': 'LPIPS-VGG perceptual term included in every arm (lambda 0.1, distillation.py:312-314) with seeded random weights -- the lpips package and its pretrained weights are un-vendored'},
+           'config': workload_config(int(os.environ.get('WORLD_SIZE', 1)), float(np.mean(calls)) if calls else None),
+           'engine': {'host': f'CPU, {port.threads} intra-op threads (fixed; the fastest count measured on the {os.cpu_count()}-thread host class); rank 0 only'},
            'whole_steps_measured': len(whole), 'extrapolated_steps': K - len(whole), 'extrapolated': len(whole) < K,
            'whole_step_s': {'min': round(min(whole.values()), 3), 'max': round(max(whole.values()), 3), 'measured_over_model_min': round(min(norm), 3),
                             'measured_over_model_max': round(max(norm), 3)},

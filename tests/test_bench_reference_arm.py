@@ -26,6 +26,12 @@ def test_reference_arm_prints_the_contract_line():
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['value'] == d['value'] and 1 <= cb['cores'] <= (os.cpu_count() or 1) and 'sample' in cb
     assert 'workload' in d['config']
+    # `config` is the workload only and is built by the SAME function the GPU arm uses (the driver compares the two arms' configs);
+    # what differs between the arms lives in `engine`
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config'] == bench.workload_config(1, d['config']['unet_evals_per_step_mean'])
+    assert set(d['config']) == {'workload', 'parallelism', 'unet_evals_per_step_mean', 'l2', 'lpips'} and 'host' in d['engine']
     # at least one WHOLE step is really run; what is filled in from measured components is declared
     assert d['whole_steps_measured'] == 1 and d['extrapolated_steps'] == 1 and d['extrapolated'] is True
     assert d['whole_step_s']['min'] > 0 and d['components_s']['per_unet_eval'] > 0
