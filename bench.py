@@ -601,16 +601,17 @@ class CpuWholeStep:
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the step = the oracle port (the reference cannot be imported on the GPU box and has
-    no CPU render path of its own), whole steps on REF_THREADS host threads.  A whole step takes 10-25 s, so only as many of the K timed steps
-    as fit the time budget are actually run (at least one); the remaining ones are filled in from the measured components of those runs with their
-    own PLMS length (n+1 UNet evaluations) -- the line says how many of each."""
+    no CPU render path of its own), whole steps on REF_THREADS host threads.  A whole step takes 10-25 s; the K timed steps are all run when they
+    fit the time budget (SFB_REF_BUDGET_S, default 420 s: K = 20 takes ~330 s, so the line's steps x ms_per_step is time really spent); on a slower
+    host only as many as fit are run (at least one) and the remaining ones are filled in from the measured components of those runs with their own
+    PLMS length (n+1 UNet evaluations) -- the line says how many of each (`whole_steps_measured`, `extrapolated_steps`, `wall_s`)."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
     thres = max_thres_sequence(W, K)
     calls = [min(int(t * 100), 50) + 1 if t >= 0.01 else 0 for t in thres[W:W + K]]
-    budget = float(os.environ.get('SFB_REF_BUDGET_S', 150))
+    budget = float(os.environ.get('SFB_REF_BUDGET_S', 420))      # 20 whole steps take ~330 s on the pool's 128-thread hosts: nothing extrapolated by default
     port = CpuWholeStep()
     t_begin = time.perf_counter()
     if W > 0:       # one short warm-up step (first-touch allocations, thread pool): 2 UNet evaluations
